@@ -32,6 +32,9 @@ namespace {
 
 typedef unsigned int u32;
 
+constexpr int SMALL_MASKS = 32;   // passes up to this size keep their tables in kernel-parameter
+constexpr int SMALL_TERMS = 96;   // (constant) memory; bigger ones read them from global memory
+
 struct PassParams {
   int nmasks;
   int B;           // log2 of the contiguous run length
@@ -47,7 +50,18 @@ struct PassParams {
   const double *cf;
   const i64 *rowoff;  // [2^(T-B)] offset of each contiguous run
   i64 rank_bits;      // global index bits contributed by the rank
+  i64 roff[16];       // offset contributed by the r-th row group of a thread
   unsigned char outer_pos[48];
+};
+
+// the same tables by value, for small passes
+struct SmallTables {
+  u32 lam[SMALL_MASKS];
+  unsigned short t_re[SMALL_MASKS], t_im[SMALL_MASKS], t_end[SMALL_MASKS];
+  u32 sw[SMALL_TERMS];
+  u32 rb[SMALL_TERMS];
+  i64 so[SMALL_TERMS];
+  double cf[SMALL_TERMS];
 };
 
 template <int T>
@@ -64,9 +78,23 @@ __device__ __forceinline__ double flip_if(int hi, int lo, u32 bits, int r)
   return __hiloint2double(hi ^ (int)((bits << (31 - r)) & 0x80000000u), lo);
 }
 
-template <int T>
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+
+__device__ __forceinline__ void cp_async_wait_all()
+{
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// One CTA = one tile of 2^T amplitudes.  Thread `tid` owns the R rows
+// l = tid + r*NT of the tile (window coordinates).
+template <int T, bool SMALL>
 __global__ void __launch_bounds__(TileCfg<T>::NT, TileCfg<T>::MINB)
-    k_tiled(const PassParams P, const cplx *__restrict__ x, cplx *__restrict__ y, const double *__restrict__ diag)
+    k_tiled(const __grid_constant__ PassParams P, const __grid_constant__ SmallTables S,
+            const cplx *__restrict__ x, cplx *__restrict__ y, const double *__restrict__ diag)
 {
   constexpr int R = TileCfg<T>::R;
   constexpr int NT = TileCfg<T>::NT;
@@ -75,30 +103,27 @@ __global__ void __launch_bounds__(TileCfg<T>::NT, TileCfg<T>::MINB)
   const int tid = threadIdx.x;
 
   // scatter the tile number into the bit positions outside the window
-  i64 outer = 0;
+  i64 base_g = 0;
   {
     const unsigned long long b = blockIdx.x;
-    for (int k = 0; k < P.n_outer; ++k) outer |= (i64)((b >> k) & 1ull) << P.outer_pos[k];
+    for (int k = 0; k < P.n_outer; ++k) base_g |= (i64)((b >> k) & 1ull) << P.outer_pos[k];
   }
-  const int lowmask = (1 << P.B) - 1;
+  const i64 outer_g = base_g | P.rank_bits;  // sign-relevant bits shared by the whole tile
+  // this thread's part of the address: its rows differ only by the uniform P.roff[r]
+  base_g |= __ldg(&P.rowoff[tid >> P.B]) | (i64)(tid & ((1 << P.B) - 1));
 
-  // stage the tile: runs of 2^B contiguous amplitudes, 16-byte loads
+  // stage the tile: runs of 2^B contiguous amplitudes, asynchronous 16-byte copies
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int l = tid + r * NT;
-    const i64 g = outer | __ldg(&P.rowoff[l >> P.B]) | (i64)(l & lowmask);
-    tile[l] = x[g];
-  }
+  for (int r = 0; r < R; ++r) cp_async16(&tile[tid + r * NT], &x[base_g | P.roff[r]]);
+  cp_async_wait_all();
   __syncthreads();
 
   double ar[R], ai[R];
   if (diag != nullptr) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int l = tid + r * NT;
-      const i64 g = outer | __ldg(&P.rowoff[l >> P.B]) | (i64)(l & lowmask);
-      const double d = diag[g];
-      const double2 v = tile[l];
+      const double d = __ldg(&diag[base_g | P.roff[r]]);
+      const double2 v = tile[tid + r * NT];
       ar[r] = d * v.x;
       ai[r] = d * v.y;
     }
@@ -107,27 +132,33 @@ __global__ void __launch_bounds__(TileCfg<T>::NT, TileCfg<T>::MINB)
     for (int r = 0; r < R; ++r) ar[r] = ai[r] = 0.0;
   }
 
-  const i64 outer_g = outer | P.rank_bits;
-
   for (int mi = 0; mi < P.nmasks; ++mi) {
-    const u32 lam = __ldg(&P.lam[mi]);
+    const u32 lam = SMALL ? S.lam[mi] : __ldg(&P.lam[mi]);
     const int base = tid ^ (int)(lam & (NT - 1));
     const int hi_l = (int)(lam >> LOG_NT);
-    const int t0 = __ldg(&P.t_re[mi]), t1 = __ldg(&P.t_im[mi]), t2 = __ldg(&P.t_end[mi]);
+    const int t0 = SMALL ? (int)S.t_re[mi] : __ldg(&P.t_re[mi]);
+    const int t1 = SMALL ? (int)S.t_im[mi] : __ldg(&P.t_im[mi]);
+    const int t2 = SMALL ? (int)S.t_end[mi] : __ldg(&P.t_end[mi]);
 #pragma unroll 1
     for (int kind = 0; kind < 2; ++kind) {
       const int ta = kind ? t1 : t0, tb = kind ? t2 : t1;
       if (ta == tb) continue;
       double d[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) d[r] = 0.0;
       for (int t = ta; t < tb; ++t) {
-        const double c = __ldg(&P.cf[t]);
-        const int p = (__popcll((unsigned long long)(__ldg(&P.so[t]) & outer_g)) ^ __popc(__ldg(&P.sw[t]) & (u32)tid)) & 1;
-        const u32 bits = __ldg(&P.rb[t]) ^ (u32)(-p);
+        const double c = SMALL ? S.cf[t] : __ldg(&P.cf[t]);
+        const i64 so = SMALL ? S.so[t] : __ldg(&P.so[t]);
+        const u32 sw = SMALL ? S.sw[t] : __ldg(&P.sw[t]);
+        const u32 rb = SMALL ? S.rb[t] : __ldg(&P.rb[t]);
+        const int p = (__popcll((unsigned long long)(so & outer_g)) ^ __popc(sw & (u32)tid)) & 1;
+        const u32 bits = rb ^ (u32)(-p);
         const int chi = __double2hiint(c), clo = __double2loint(c);
+        if (t == ta) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) d[r] += flip_if(chi, clo, bits, r);
+          for (int r = 0; r < R; ++r) d[r] = flip_if(chi, clo, bits, r);
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) d[r] += flip_if(chi, clo, bits, r);
+        }
       }
       if (kind == 0) {
 #pragma unroll
@@ -151,17 +182,20 @@ __global__ void __launch_bounds__(TileCfg<T>::NT, TileCfg<T>::MINB)
     }
   }
 
+  if (P.accumulate) {
+    // reuse the tile buffer to fetch the previous pass's y with full memory-level parallelism
+    __syncthreads();
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int l = tid + r * NT;
-    const i64 g = outer | __ldg(&P.rowoff[l >> P.B]) | (i64)(l & lowmask);
-    double2 o = make_double2(ar[r], ai[r]);
-    if (P.accumulate) {
-      const double2 old = y[g];
-      o.x += old.x;
-      o.y += old.y;
+    for (int r = 0; r < R; ++r) cp_async16(&tile[tid + r * NT], &y[base_g | P.roff[r]]);
+    cp_async_wait_all();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double2 old = tile[tid + r * NT];  // written by this thread's own copies
+      y[base_g | P.roff[r]] = make_double2(ar[r] + old.x, ai[r] + old.y);
     }
-    y[g] = o;
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) y[base_g | P.roff[r]] = make_double2(ar[r], ai[r]);
   }
 }
 
@@ -295,6 +329,8 @@ struct NMask {
 
 struct Pass {
   PassParams p{};
+  SmallTables st{};
+  bool small = false;
   int T = 0;
   int peer_xor = 0;  // x is read from rank ^ peer_xor
   int nterms = 0;
@@ -486,7 +522,24 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
   ps.p.cf = up(cf, ps.owned);
   ps.p.rowoff = up(rowoff, ps.owned);
   ps.p.rank_bits = (i64)G.rank << nloc;
+  for (int r = 0; r < 16; ++r) ps.p.roff[r] = 0;
+  for (int r = 0; r < R; ++r) ps.p.roff[r] = rowoff[((size_t)r << log_nt) >> B];
   ps.nterms = (int)flat.size();
+  ps.small = (int)masks.size() <= SMALL_MASKS && ps.nterms <= SMALL_TERMS;
+  if (ps.small) {
+    for (size_t k = 0; k < masks.size(); ++k) {
+      ps.st.lam[k] = lam[k];
+      ps.st.t_re[k] = (unsigned short)t_re[k];
+      ps.st.t_im[k] = (unsigned short)t_im[k];
+      ps.st.t_end[k] = (unsigned short)t_end[k];
+    }
+    for (int t = 0; t < ps.nterms; ++t) {
+      ps.st.sw[t] = sw[t];
+      ps.st.rb[t] = rb[t];
+      ps.st.so[t] = so[t];
+      ps.st.cf[t] = cf[t];
+    }
+  }
   return ps;
 }
 
@@ -570,18 +623,26 @@ struct PlanInputs {
   std::vector<NMask> masks;
 };
 
-template <int T>
-void launch_tiled(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
+template <int T, bool SMALL>
+void launch_tiled_v(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
 {
   static bool attr_set = false;
   const size_t smem = sizeof(double2) << T;
   if (!attr_set) {
-    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled<T, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled<T, SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
-  k_tiled<T><<<(unsigned)ntiles, TileCfg<T>::NT, smem, G.stream>>>(ps.p, x, y, diag);
+  k_tiled<T, SMALL><<<(unsigned)ntiles, TileCfg<T>::NT, smem, G.stream>>>(ps.p, ps.st, x, y, diag);
   count_launch();
   DNM_CHECK_CUDA(cudaGetLastError());
+}
+
+template <int T>
+void launch_tiled(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
+{
+  if (ps.small) launch_tiled_v<T, true>(ps, x, y, diag, ntiles);
+  else launch_tiled_v<T, false>(ps, x, y, diag, ntiles);
 }
 
 int direct_grid(i64 rows)
@@ -632,6 +693,7 @@ TiledPlan *build_plan(dnm_mat_s *A)
   } else {
     int B = std::min(3, T - 1);
     if (const char *e = getenv("DNM_TILE_RUN_BITS")) B = std::max(0, std::min(atoi(e), T - 1));
+    B = std::min(B, (T >= 10) ? T - 4 : 6);  // a thread's own index bits must cover the run bits
     bool first = true;
     for (auto &kv : groups) {
       plan_group(*plan, kv.second, kv.first, T, B, first, A->verbose);

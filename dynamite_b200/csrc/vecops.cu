@@ -52,8 +52,9 @@ __device__ __forceinline__ void block_reduce_store(const double (&acc)[NV], doub
 
 // d_out[c] = reduce_b partials[b*nv + c]
 __global__ void k_final_reduce(const double *__restrict__ partials, int nblocks, int nv, double *__restrict__ d_out,
-                               int is_max)
+                               int is_max, const int *__restrict__ active)
 {
+  if (active != nullptr && *active == 0) return;
   __shared__ double sh[TPB / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int c = 0; c < nv; ++c) {
@@ -132,8 +133,9 @@ __global__ void k_absnorm(const cplx *__restrict__ x, int64_t n, double *__restr
 // NV vectors against one w: each thread reads w[i] once and V_j[i] for every j.
 template <int NV>
 __global__ void __launch_bounds__(TPB) k_multi_dot(VecList vs, const cplx *__restrict__ w, int64_t n,
-                                                   double *__restrict__ partials)
+                                                   double *__restrict__ partials, const int *__restrict__ active)
 {
+  if (active != nullptr && *active == 0) return;
   double acc[2 * NV];
 #pragma unroll
   for (int c = 0; c < 2 * NV; ++c) acc[c] = 0.0;
@@ -151,8 +153,10 @@ __global__ void __launch_bounds__(TPB) k_multi_dot(VecList vs, const cplx *__res
 
 template <int NV, bool WITH_NORM>
 __global__ void __launch_bounds__(TPB) k_multi_axpy_sub(VecList vs, cplx *__restrict__ w, int64_t n,
-                                                        const double *__restrict__ d_h, double *__restrict__ partials)
+                                                        const double *__restrict__ d_h, double *__restrict__ partials,
+                                                        const int *__restrict__ active)
 {
+  if (active != nullptr && *active == 0) return;
   double hr[NV], hi[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
@@ -226,9 +230,9 @@ double *partials_for(int nblocks, int nv)
   return G.d_partials;
 }
 
-void finish(int nblocks, int nv, double *d_out, bool is_max)
+void finish(int nblocks, int nv, double *d_out, bool is_max, const int *d_active = nullptr)
 {
-  k_final_reduce<<<1, TPB, 0, G.stream>>>(G.d_partials, nblocks, nv, d_out, is_max ? 1 : 0);
+  k_final_reduce<<<1, TPB, 0, G.stream>>>(G.d_partials, nblocks, nv, d_out, is_max ? 1 : 0, d_active);
   count_launch();
   DNM_CHECK_CUDA(cudaGetLastError());
   if (is_max) allreduce_max_dev(d_out, nv);
@@ -236,28 +240,28 @@ void finish(int nblocks, int nv, double *d_out, bool is_max)
 }
 
 template <int NV>
-void launch_multi_dot(const VecList &vs, const cplx *w, int64_t n, double *d_h)
+void launch_multi_dot(const VecList &vs, const cplx *w, int64_t n, double *d_h, const int *d_active)
 {
   const int g = reduce_grid(n);
   double *p = partials_for(g, 2 * NV);
-  k_multi_dot<NV><<<g, TPB, 0, G.stream>>>(vs, w, n, p);
+  k_multi_dot<NV><<<g, TPB, 0, G.stream>>>(vs, w, n, p, d_active);
   count_launch();
   DNM_CHECK_CUDA(cudaGetLastError());
-  finish(g, 2 * NV, d_h, false);
+  finish(g, 2 * NV, d_h, false, d_active);
 }
 
 template <int NV>
-void launch_multi_axpy(const VecList &vs, cplx *w, int64_t n, const double *d_h, double *d_sq)
+void launch_multi_axpy(const VecList &vs, cplx *w, int64_t n, const double *d_h, double *d_sq, const int *d_active)
 {
   const int g = reduce_grid(n);
   if (d_sq) {
     double *p = partials_for(g, 1);
-    k_multi_axpy_sub<NV, true><<<g, TPB, 0, G.stream>>>(vs, w, n, d_h, p);
+    k_multi_axpy_sub<NV, true><<<g, TPB, 0, G.stream>>>(vs, w, n, d_h, p, d_active);
     count_launch();
     DNM_CHECK_CUDA(cudaGetLastError());
-    finish(g, 1, d_sq, false);
+    finish(g, 1, d_sq, false, d_active);
   } else {
-    k_multi_axpy_sub<NV, false><<<g, TPB, 0, G.stream>>>(vs, w, n, d_h, nullptr);
+    k_multi_axpy_sub<NV, false><<<g, TPB, 0, G.stream>>>(vs, w, n, d_h, nullptr, d_active);
     count_launch();
     DNM_CHECK_CUDA(cudaGetLastError());
   }
@@ -363,14 +367,14 @@ void vec_norm_other_dev(const cplx *x, int64_t n, int type, double *d_out)
   finish(g, 1, d_out, type == 2);
 }
 
-void multi_dot_dev(const VecList &vs, const cplx *w, int64_t n, double *d_h)
+void multi_dot_dev(const VecList &vs, const cplx *w, int64_t n, double *d_h, const int *d_active)
 {
-  DNM_DISPATCH_NV(vs.n, launch_multi_dot<NV>(vs, w, n, d_h));
+  DNM_DISPATCH_NV(vs.n, launch_multi_dot<NV>(vs, w, n, d_h, d_active));
 }
 
-void multi_axpy_sub_dev(const VecList &vs, cplx *w, int64_t n, const double *d_h, double *d_sq)
+void multi_axpy_sub_dev(const VecList &vs, cplx *w, int64_t n, const double *d_h, double *d_sq, const int *d_active)
 {
-  DNM_DISPATCH_NV(vs.n, launch_multi_axpy<NV>(vs, w, n, d_h, d_sq));
+  DNM_DISPATCH_NV(vs.n, launch_multi_axpy<NV>(vs, w, n, d_h, d_sq, d_active));
 }
 
 void multi_combine_dev(const VecList &vs, cplx *out, int64_t n, const double *d_c)

@@ -33,9 +33,11 @@ void vec_norm_other_dev(const cplx *x, int64_t n, int type, double *d_out);
 
 // h[j] = sum_i conj(V_j[i]) * w[i], j < vs.n           (global over ranks)
 // d_h: vs.n complex (interleaved) on the device
-void multi_dot_dev(const VecList &vs, const cplx *w, int64_t n, double *d_h);
+// d_active (optional, device int): when it points to 0 the launch is a no-op
+void multi_dot_dev(const VecList &vs, const cplx *w, int64_t n, double *d_h, const int *d_active = nullptr);
 // w -= sum_j h[j] * V_j ;  d_sq[0] = ||w_new||^2 if d_sq != nullptr (global)
-void multi_axpy_sub_dev(const VecList &vs, cplx *w, int64_t n, const double *d_h, double *d_sq);
+void multi_axpy_sub_dev(const VecList &vs, cplx *w, int64_t n, const double *d_h, double *d_sq,
+                        const int *d_active = nullptr);
 // out = sum_j c[j] * V_j   (c on device, complex); out may alias V_0
 void multi_combine_dev(const VecList &vs, cplx *out, int64_t n, const double *d_c);
 // out += sum_j c[j] * V_j

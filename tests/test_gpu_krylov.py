@@ -1,0 +1,244 @@
+"""GPU parity of the Krylov consumers (evolve, eigsolve) and rdm.
+Oracles: the golden fixtures (scipy expm_multiply / numpy eigvalsh applied to the
+reference's own matrices), scipy on the fly for bigger cases, and oracle.rdm.
+Tolerances: evolve states and eigenvalues 1e-10 (north star)."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg
+
+import oracle
+from helpers import case_terms, golden_cases, kats, product_subspace, rand_state, rel_err
+
+pytestmark = pytest.mark.gpu
+CASES = golden_cases()
+
+
+def operator_for(tag):
+    """dynamite_b200 Operator + subspace + input State for a golden case"""
+    from dynamite_b200.operators import Operator
+    from dynamite_b200.states import State
+    from dynamite_b200.subspaces import Full, XParity
+    c = CASES[tag]
+    L = c['left']['L']
+    if c['xparity']:
+        # golden MSC is already reduced; rebuild the unreduced operator from its name
+        from dynamite_b200.hamiltonians import build_hamiltonian
+        H = build_hamiltonian(tag.split('_')[0], L)
+        sub = XParity(Full(L=L), sector='+' if tag.endswith('plus') else '-')
+    else:
+        H = Operator(msc=case_terms(c), L=L)
+        sub = product_subspace(c['left'])
+    H.allow_projection = True
+    H.subspace = sub
+    x = State(L=L, subspace=sub)
+    x.vec[0:len(c['x'])] = c['x']
+    x.set_initialized()
+    return c, H, sub, x
+
+
+EVOLVE_TAGS = sorted(t for t in CASES if 'evolved' in CASES[t])
+
+
+@pytest.mark.parametrize('tag', EVOLVE_TAGS)
+def test_evolve_vs_golden(gpu, tag):
+    c, H, sub, x = operator_for(tag)
+    t = float(c['evolve_t'])
+    y = H.evolve(x, t, tol=1e-13)
+    assert rel_err(y.to_numpy(), c['evolved']) < 1e-10
+    assert abs(y.norm() - 1.0) < 1e-10
+    # imaginary time (real scale): exp(-t H) x
+    yi = H.evolve(x, -1j * t, tol=1e-13)
+    assert rel_err(yi.to_numpy(), c['evolved_imag']) < 1e-10
+    # default tolerance (1e-7) is what the reference's tests use with a 1e-9 overlap check
+    yd = H.evolve(x, t)
+    ov = np.vdot(c['evolved'], yd.to_numpy())
+    assert abs(1 - ov) < 1e-7
+    # backwards in time returns to the start
+    back = H.evolve(y, -t, tol=1e-13)
+    assert rel_err(back.to_numpy(), c['x']) < 1e-10
+
+
+@pytest.mark.parametrize('name,L,ncv', [('MBL', 14, None), ('long_range', 13, 12), ('heisenberg', 15, 40), ('ising', 12, 5)])
+def test_evolve_vs_scipy(gpu, name, L, ncv):
+    from dynamite_b200.hamiltonians import build_hamiltonian
+    from dynamite_b200.states import State
+    H = build_hamiltonian(name, L)
+    x = State(L=L, state='random', seed=3)
+    A = H.to_numpy()
+    nrm = H.infinity_norm()
+    assert abs(nrm - abs(A).sum(axis=1).max()) < 1e-11 * nrm
+    for t in (1.0 / nrm, 7.0, 50.0 / nrm):
+        want = scipy.sparse.linalg.expm_multiply(-1j * t * A, x.to_numpy())
+        got = H.evolve(x, t, tol=1e-12, ncv=ncv)
+        assert rel_err(got.to_numpy(), want) < 1e-10, (name, t)
+
+
+def test_evolve_edge_cases(gpu):
+    from dynamite_b200.computations import MaxIterationsError
+    from dynamite_b200.hamiltonians import build_hamiltonian
+    from dynamite_b200.operators import sigmax, sigmaz, index_sum
+    from dynamite_b200.states import State
+    from dynamite_b200.subspaces import Parity
+    H = build_hamiltonian('long_range', 10)
+    x = State(L=10, state='random', seed=1)
+    # t = 0 is a copy
+    assert np.array_equal(H.evolve(x, 0.0).to_numpy(), x.to_numpy())
+    # too few iterations for a long evolution (reference test_evolve.py:195-202)
+    with pytest.raises(MaxIterationsError):
+        H.evolve(x, 500.0, max_its=2)
+    # result vector reuse and subspace mismatch
+    y = State(L=10)
+    H.evolve(x, 0.3, result=y)
+    with pytest.raises(ValueError):
+        H.evolve(x, 0.3, result=State(L=10, subspace=Parity('even', L=10)))
+    # pi pulse: exp(-i (pi/2) sum sigma_x) flips every spin (reference test_evolve.py:23-32)
+    L = 8
+    Hx = index_sum(sigmax(), size=L)
+    Hx.L = L
+    s = State(L=L, state='U' * L)
+    out = Hx.evolve(s, np.pi / 2, tol=1e-12).to_numpy()
+    want = np.zeros(1 << L, complex)
+    want[-1] = (-1j) ** L
+    assert np.allclose(out, want, atol=1e-10)
+    # tiny dimension: Krylov space is exhausted (happy breakdown)
+    Hz = sigmaz(0) + 0.5 * sigmax(0) * sigmax(1)
+    Hz.L = 2
+    s2 = State(L=2, state='random', seed=5)
+    A = Hz.to_numpy(sparse=False)
+    want = scipy.linalg.expm(-1j * 2.5 * A) @ s2.to_numpy()
+    assert np.allclose(Hz.evolve(s2, 2.5).to_numpy(), want, atol=1e-10)
+    # an eigenstate only picks up a phase (invariant subspace of dimension 1)
+    Hd = index_sum(sigmaz(0) * sigmaz(1), size=6)
+    Hd.L = 6
+    e = State(L=6, state='UDUDUD')
+    assert np.allclose(Hd.evolve(e, 1.7).to_numpy(), np.exp(-1j * 1.7 * -5) * e.to_numpy(), atol=1e-12)
+
+
+EIG_TAGS = sorted(t for t in CASES if 'evals' in CASES[t])
+
+
+@pytest.mark.parametrize('tag', EIG_TAGS)
+def test_eigsolve_vs_golden(gpu, tag):
+    c, H, sub, x = operator_for(tag)
+    w = c['evals']
+    n = w.size
+    nev = min(4, n)
+    for which, want in (('lowest', w[:nev]), ('highest', w[::-1][:nev]),
+                        ('exterior', w[np.argsort(-np.abs(w), kind='stable')][:nev])):
+        evals, evecs = H.eigsolve(nev=nev, which=which, getvecs=True, tol=1e-12)
+        assert len(evals) >= nev
+        scale = max(1.0, np.max(np.abs(w)))
+        # Krylov methods may miss copies of a degenerate eigenvalue (documented in the
+        # reference, computations.py:139-142): compare the DISTINCT values, in order,
+        # and require every returned value to be a true eigenvalue.
+        def distinct(vals):
+            out = []
+            for v in vals:
+                if not out or abs(v - out[-1]) > 1e-8 * scale:
+                    out.append(v)
+            return np.array(out)
+        key = (lambda v: -np.abs(v)) if which == 'exterior' else (lambda v: v if which == 'lowest' else -v)
+        got_d = distinct(sorted(evals[:nev], key=key))
+        want_d = distinct(sorted(w, key=key))[:got_d.size]
+        if which == 'exterior':
+            assert np.allclose(np.abs(got_d), np.abs(want_d), atol=1e-10 * scale), (tag, which, evals, want)
+        else:
+            assert np.allclose(got_d, want_d, atol=1e-10 * scale), (tag, which, evals, want)
+        for lam in evals[:nev]:
+            assert np.min(np.abs(w - lam)) < 1e-10 * scale
+        A = c['A']
+        V = np.array([v.to_numpy() for v in evecs[:nev]])
+        for lam, v in zip(evals[:nev], V):
+            assert abs(np.linalg.norm(v) - 1) < 1e-10
+            assert np.linalg.norm(A @ v - lam * v) < 1e-8 * scale
+        # orthonormal even inside degenerate multiplets
+        assert np.allclose(V.conj() @ V.T, np.eye(nev), atol=1e-8)
+
+
+def test_eigsolve_larger_and_errors(gpu):
+    from dynamite_b200.computations import MaxIterationsError
+    from dynamite_b200.hamiltonians import build_hamiltonian
+    from dynamite_b200.operators import index_sum, sigmax
+    from dynamite_b200.subspaces import SpinConserve, XParity
+    L = 14
+    H = build_hamiltonian('heisenberg', L)
+    H.subspace = SpinConserve(L, L // 2)
+    A = H.to_numpy()
+    want = scipy.sparse.linalg.eigsh(A, k=5, which='SA')[0]
+    want.sort()
+    evals, evecs = H.eigsolve(nev=5, getvecs=True, tol=1e-12)
+    assert np.allclose(evals[:5], want, atol=1e-10)
+    for lam, v in zip(evals[:5], evecs[:5]):
+        assert np.linalg.norm(A @ v.to_numpy() - lam * v.to_numpy()) < 1e-8
+    # default tolerance
+    e1 = H.eigsolve()
+    assert abs(e1[0] - want[0]) < 1e-7
+    # XParity on top of SpinConserve: the ground state lives in one of the two sectors
+    lows = []
+    for sector in '+-':
+        Hx = build_hamiltonian('heisenberg', L)
+        Hx.subspace = XParity(SpinConserve(L, L // 2), sector=sector)
+        lows.append(Hx.eigsolve(nev=1, tol=1e-12)[0])
+    assert abs(min(lows) - want[0]) < 1e-10
+    # analytic spectrum of sum sigma_x: -L, -L+2, ... (reference test_eigsolve.py:95-123)
+    Hs = index_sum(sigmax(), size=8)
+    Hs.L = 8
+    ev = Hs.eigsolve(nev=1, tol=1e-12)
+    assert abs(ev[0] + 8) < 1e-10
+    assert abs(Hs.eigsolve(nev=1, which='highest', tol=1e-12)[0] - 8) < 1e-10
+    with pytest.raises(RuntimeError):
+        H.eigsolve(target=0.1)
+    with pytest.raises(MaxIterationsError):
+        build_hamiltonian('MBL', 12).eigsolve(nev=6, tol=1e-14, max_its=2)
+
+
+def test_rdm_kats_and_oracle(gpu):
+    from dynamite_b200.computations import entanglement_entropy, reduced_density_matrix
+    from dynamite_b200.states import State
+    from dynamite_b200.subspaces import Full, XParity
+    k = kats()
+    psi = np.array([complex(*v) for v in k['rdm_L4_state']])
+    s = State(L=4)
+    s.vec[0:16] = psi
+    s.set_initialized()
+    for keep, key in (([0], 'rdm_L4_keep0'), ([2], 'rdm_L4_keep2')):
+        want = np.array([[complex(*v) for v in row] for row in k[key]])
+        got = reduced_density_matrix(s, keep)
+        assert np.allclose(got, want, atol=2e-6)
+        assert abs(entanglement_entropy(s, keep) - k[key + '_entropy']) < 2e-5
+    for keep, key in (([0, 2], 'rdm_L4_keep02_entropy'), ([1, 3], 'rdm_L4_keep13_entropy')):
+        assert abs(entanglement_entropy(s, keep) - k[key]) < 2e-5
+    full4 = oracle.Subspace({'type': 'full', 'L': 4})
+    for keep in ([], [0], [3], [0, 1], [1, 2, 3], [0, 1, 2, 3]):
+        assert np.allclose(reduced_density_matrix(s, keep), oracle.rdm(psi, full4, keep), atol=1e-14)
+    cs = k['rdm_complex_sign']
+    s2 = State(L=2)
+    s2.vec[0:4] = np.array([complex(*v) for v in cs['state']])
+    s2.set_initialized()
+    assert np.array_equal(reduced_density_matrix(s2, cs['keep']),
+                          np.array([[complex(*v) for v in row] for row in cs['dm']]))
+    with pytest.raises(ValueError):
+        reduced_density_matrix(s, [2, 1])
+    with pytest.raises(ValueError):
+        reduced_density_matrix(State(subspace=XParity(Full(L=4)), state='uniform'), [0])
+
+
+@pytest.mark.parametrize('spec', [
+    {'type': 'full', 'L': 13}, {'type': 'parity', 'L': 12, 'space': 1}, {'type': 'spinconserve', 'L': 14, 'k': 6},
+    {'type': 'explicit', 'L': 10, 'states': list(range(5, 900, 3))},
+])
+def test_rdm_subspaces_vs_oracle(gpu, spec):
+    from dynamite_b200.computations import reduced_density_matrix
+    from dynamite_b200.states import State
+    sub = product_subspace(spec)
+    osub = oracle.Subspace(spec)
+    psi = rand_state(osub.dim, 13)
+    s = State(subspace=sub)
+    s.vec[0:osub.dim] = psi
+    s.set_initialized()
+    L = spec['L']
+    for keep in ([0], [L - 1], [0, 1, 2], [1, 4, L - 2], list(range(0, L // 2)), list(range(L - 6, L))):
+        got = reduced_density_matrix(s, keep)
+        want = oracle.rdm(psi, osub, keep)
+        assert np.allclose(got, want, atol=1e-13), keep
+        assert abs(np.trace(got) - 1) < 1e-12

@@ -139,7 +139,8 @@ def test_device_index_maps_bit_exact(gpu):
     lib = gpu.lib()
     for spec in specs:
         orc = oracle.Subspace(spec)
-        desc = product_subspace(spec)._to_c()['data'].desc
+        cdata = product_subspace(spec)._to_c()['data']   # keep the arrays behind the descriptor alive
+        desc = cdata.desc
         dim = orc.dim
         idx = np.unique(np.concatenate([R.randint(0, dim, 20000), [0, dim - 1]])).astype(np.int64)
         states = np.empty_like(idx)
