@@ -54,6 +54,8 @@ _SIGNATURES = {
     'dnm_timer_stop': (C.c_int, [C.POINTER(C.c_float)]),
     'dnm_mem_info': (C.c_int, [i64p, i64p]),
     'dnm_launch_count': (C.c_int64, [C.c_int]),
+    'dnm_host_alloc': (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    'dnm_host_free': (C.c_int, [C.c_void_p]),
     'dnm_comm_unique_id': (C.c_int, [C.c_char_p]),
     'dnm_comm_init': (C.c_int, [C.c_int, C.c_int, C.c_char_p]),
     'dnm_comm_rank': (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -74,6 +76,7 @@ _SIGNATURES = {
     'dnm_vec_set_values': (C.c_int, [_vec, C.c_int64, i64p, f64p, C.c_int]),
     'dnm_vec_get_values': (C.c_int, [_vec, C.c_int64, i64p, f64p]),
     'dnm_vec_set': (C.c_int, [_vec, C.c_double, C.c_double]),
+    'dnm_vec_set_random': (C.c_int, [_vec, C.c_uint64]),
     'dnm_vec_copy': (C.c_int, [_vec, _vec]),
     'dnm_vec_scale': (C.c_int, [_vec, C.c_double, C.c_double]),
     'dnm_vec_axpby': (C.c_int, [_vec, C.c_double, C.c_double, C.c_double, C.c_double, _vec]),

@@ -146,8 +146,10 @@ struct dnm_mat_s {
   double nrm = -1;
   int kernel_pref = 0;  // 0 auto, 1 general, 2 tiled
   int tile_bits = 0;    // 0 auto
+  int tile_rows = 0;    // rows per thread in the tiled kernel: 0 auto, 8 or 16
   int verbose = 0;
   dnm::TiledPlan *tiled = nullptr;
   int launches_per_mult = 0;
   int kernel_used = 0;
+  dnm_vec_t work_x = nullptr, work_y = nullptr;  // device staging for dnm_mat_mult_host
 };

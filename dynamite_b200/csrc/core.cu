@@ -216,6 +216,24 @@ extern "C" int64_t dnm_launch_count(int reset)
   return v;
 }
 
+extern "C" int dnm_host_alloc(int64_t bytes, void **out)
+{
+  DNM_API_BEGIN
+  require_init();
+  DNM_REQUIRE(out && bytes > 0, DNM_ERR_ARG, "bad arguments to dnm_host_alloc");
+  void *p = nullptr;
+  DNM_CHECK_CUDA(cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault));
+  *out = p;
+  DNM_API_END
+}
+
+extern "C" int dnm_host_free(void *ptr)
+{
+  DNM_API_BEGIN
+  if (ptr) DNM_CHECK_CUDA(cudaFreeHost(ptr));
+  DNM_API_END
+}
+
 // ---- communicator --------------------------------------------------------------
 
 extern "C" int dnm_comm_unique_id(char id[128])
@@ -572,6 +590,15 @@ extern "C" int dnm_vec_set(dnm_vec_t v, double re, double im)
   require_init();
   DNM_REQUIRE(v, DNM_ERR_ARG, "null vector");
   vec_fill(v->d, v->local_n, make_double2(re, im));
+  DNM_API_END
+}
+
+extern "C" int dnm_vec_set_random(dnm_vec_t v, uint64_t seed)
+{
+  DNM_API_BEGIN
+  require_init();
+  DNM_REQUIRE(v, DNM_ERR_ARG, "null vector");
+  vec_random_fill(v->d, v->local_n, v->local_start, seed);
   DNM_API_END
 }
 

@@ -78,23 +78,6 @@ __global__ void k_col_second(const double *__restrict__ d_h2, int nh, const doub
 
 __global__ void k_sqrt_inplace(double *v) { *v = sqrt(*v); }
 
-// counter-based Gaussian-ish start vector (uniform in [-1,1]^2 per entry)
-__global__ void k_random_fill(cplx *__restrict__ v, int64_t n, int64_t offset, uint64_t seed)
-{
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    uint64_t z = (uint64_t)(i + offset) * 0x9E3779B97F4A7C15ull + seed * 0xD1B54A32D192ED03ull + 0x632BE59BD9B4E019ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    uint64_t z2 = z * 0x9E3779B97F4A7C15ull + 0x7F4A7C15ull;
-    z2 = (z2 ^ (z2 >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z2 ^= z2 >> 29;
-    const double a = (double)(z >> 11) * (1.0 / 9007199254740992.0);
-    const double b = (double)(z2 >> 11) * (1.0 / 9007199254740992.0);
-    v[i] = make_double2(2.0 * a - 1.0, 2.0 * b - 1.0);
-  }
-}
-
 // V[:, first : first+nout] <- V[:, first : first+nin] * Q   (Q real, nin x nout, column-major)
 // in place: every row block is staged in shared memory before anything is written.
 constexpr int ROT_ROWS = 64;
@@ -463,9 +446,7 @@ extern "C" int dnm_eigsolve(dnm_mat_t A, int nev, int which, double tol, int max
 
   auto random_unit = [&](int col, int northo) {
     // random vector, orthogonalised (twice) against v[0..northo), normalised
-    k_random_fill<<<stream_blocks(nloc, 256), 256, 0, G.stream>>>(B.ptr(col), nloc, (int64_t)G.rank * nloc,
-                                                                  seed + 7919ull * (uint64_t)col);
-    count_launch();
+    vec_random_fill(B.ptr(col), nloc, (int64_t)G.rank * nloc, seed + 7919ull * (uint64_t)col);
     for (int rep = 0; rep < 2 && northo > 0; ++rep) {
       fused_dots(B, northo, B.ptr(col), S.h, nullptr);
       fused_axpys(B, northo, B.ptr(col), S.h, nullptr, nullptr);

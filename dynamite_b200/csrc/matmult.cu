@@ -323,6 +323,8 @@ extern "C" int dnm_mat_destroy(dnm_mat_t A)
   if (!A) return DNM_OK;
   if (G.inited) cudaStreamSynchronize(G.stream);
   tiled_free(A);
+  if (A->work_x) dnm_vec_destroy(A->work_x);
+  if (A->work_y) dnm_vec_destroy(A->work_y);
   for (void *p : A->owned) cudaFree(p);
   if (A->d_diag) cudaFree(A->d_diag);
   A->left.release();
@@ -391,23 +393,19 @@ extern "C" int dnm_mat_mult_host(dnm_mat_t A, const double *x_host, double *y_ho
   require_init();
   DNM_REQUIRE(A && x_host && y_host, DNM_ERR_ARG, "null pointer");
   DNM_REQUIRE(G.nranks == 1, DNM_ERR_UNSUPPORTED, "dnm_mat_mult_host is single-rank");
-  dnm_vec_t x = nullptr, y = nullptr;
-  int rc = dnm_vec_create(A->N, &x);
-  if (rc) return rc;
-  rc = dnm_vec_create(A->M, &y);
-  if (rc) {
-    dnm_vec_destroy(x);
-    return rc;
+  if (!A->work_x) {
+    int rc = dnm_vec_create(A->N, &A->work_x);
+    if (rc) return rc;
   }
-  DNM_CHECK_CUDA(cudaMemcpyAsync(x->d, x_host, sizeof(cplx) * A->N, cudaMemcpyHostToDevice, G.stream));
-  rc = dnm_mat_mult(A, x, y);
-  if (rc == 0) {
-    DNM_CHECK_CUDA(cudaMemcpyAsync(y_host, y->d, sizeof(cplx) * A->M, cudaMemcpyDeviceToHost, G.stream));
-    DNM_CHECK_CUDA(cudaStreamSynchronize(G.stream));
+  if (!A->work_y) {
+    int rc = dnm_vec_create(A->M, &A->work_y);
+    if (rc) return rc;
   }
-  dnm_vec_destroy(x);
-  dnm_vec_destroy(y);
+  DNM_CHECK_CUDA(cudaMemcpyAsync(A->work_x->d, x_host, sizeof(cplx) * A->N, cudaMemcpyHostToDevice, G.stream));
+  int rc = dnm_mat_mult(A, A->work_x, A->work_y);
   if (rc) return rc;
+  DNM_CHECK_CUDA(cudaMemcpyAsync(y_host, A->work_y->d, sizeof(cplx) * A->M, cudaMemcpyDeviceToHost, G.stream));
+  DNM_CHECK_CUDA(cudaStreamSynchronize(G.stream));
   DNM_API_END
 }
 
@@ -456,6 +454,10 @@ extern "C" int dnm_mat_set_option(dnm_mat_t A, const char *key, int64_t value)
   } else if (!strcmp(key, "tile_bits")) {
     DNM_REQUIRE(value == 0 || (value >= 8 && value <= 13), DNM_ERR_ARG, "tile_bits must be 0 (auto) or in [8,13]");
     A->tile_bits = (int)value;
+    tiled_free(A);
+  } else if (!strcmp(key, "tile_rows")) {
+    DNM_REQUIRE(value == 0 || value == 8 || value == 16, DNM_ERR_ARG, "tile_rows must be 0 (auto), 8 or 16");
+    A->tile_rows = (int)value;
     tiled_free(A);
   } else if (!strcmp(key, "verbose")) {
     A->verbose = (int)value;

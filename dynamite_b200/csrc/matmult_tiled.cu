@@ -24,180 +24,14 @@
 #include <map>
 #include <memory>
 
+#include "tiled_kernel.cuh"
 #include "vecops.cuh"
 
 namespace dnm {
 
 namespace {
 
-typedef unsigned int u32;
-
-constexpr int SMALL_MASKS = 32;   // passes up to this size keep their tables in kernel-parameter
-constexpr int SMALL_TERMS = 96;   // (constant) memory; bigger ones read them from global memory
-
-struct PassParams {
-  int nmasks;
-  int B;           // log2 of the contiguous run length
-  int n_outer;     // number of index bits outside the window
-  int accumulate;  // 0: y = ..., 1: y += ...
-  const u32 *lam;  // [nmasks] mask in window coordinates
-  const int *t_re; // [nmasks] first real term
-  const int *t_im; // [nmasks] first imaginary term
-  const int *t_end;
-  const u32 *sw;   // [nterms] sign bits inside the window (window coordinates)
-  const u32 *rb;   // [nterms] bit r = parity((sw >> LOG_NT) & r)
-  const i64 *so;   // [nterms] sign bits outside the window (global index coordinates)
-  const double *cf;
-  const i64 *rowoff;  // [2^(T-B)] offset of each contiguous run
-  i64 rank_bits;      // global index bits contributed by the rank
-  i64 roff[16];       // offset contributed by the r-th row group of a thread
-  unsigned char outer_pos[48];
-};
-
-// the same tables by value, for small passes
-struct SmallTables {
-  u32 lam[SMALL_MASKS];
-  unsigned short t_re[SMALL_MASKS], t_im[SMALL_MASKS], t_end[SMALL_MASKS];
-  u32 sw[SMALL_TERMS];
-  u32 rb[SMALL_TERMS];
-  i64 so[SMALL_TERMS];
-  double cf[SMALL_TERMS];
-};
-
-template <int T>
-struct TileCfg {
-  static constexpr int R = (T >= 10) ? 16 : (T == 9 ? 8 : 4);
-  static constexpr int NT = (1 << T) / R;
-  static constexpr int LOG_NT = (T >= 10) ? T - 4 : (T == 9 ? 6 : 6);
-  static constexpr int MINB = (T >= 13) ? 1 : 2;
-};
-
-__device__ __forceinline__ double flip_if(int hi, int lo, u32 bits, int r)
-{
-  // negate when bit r of `bits` is set: xor into the IEEE sign bit
-  return __hiloint2double(hi ^ (int)((bits << (31 - r)) & 0x80000000u), lo);
-}
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
-{
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
-}
-
-__device__ __forceinline__ void cp_async_wait_all()
-{
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
-
-// One CTA = one tile of 2^T amplitudes.  Thread `tid` owns the R rows
-// l = tid + r*NT of the tile (window coordinates).
-template <int T, bool SMALL>
-__global__ void __launch_bounds__(TileCfg<T>::NT, TileCfg<T>::MINB)
-    k_tiled(const __grid_constant__ PassParams P, const __grid_constant__ SmallTables S,
-            const cplx *__restrict__ x, cplx *__restrict__ y, const double *__restrict__ diag)
-{
-  constexpr int R = TileCfg<T>::R;
-  constexpr int NT = TileCfg<T>::NT;
-  constexpr int LOG_NT = TileCfg<T>::LOG_NT;
-  extern __shared__ double2 tile[];
-  const int tid = threadIdx.x;
-
-  // scatter the tile number into the bit positions outside the window
-  i64 base_g = 0;
-  {
-    const unsigned long long b = blockIdx.x;
-    for (int k = 0; k < P.n_outer; ++k) base_g |= (i64)((b >> k) & 1ull) << P.outer_pos[k];
-  }
-  const i64 outer_g = base_g | P.rank_bits;  // sign-relevant bits shared by the whole tile
-  // this thread's part of the address: its rows differ only by the uniform P.roff[r]
-  base_g |= __ldg(&P.rowoff[tid >> P.B]) | (i64)(tid & ((1 << P.B) - 1));
-
-  // stage the tile: runs of 2^B contiguous amplitudes, asynchronous 16-byte copies
-#pragma unroll
-  for (int r = 0; r < R; ++r) cp_async16(&tile[tid + r * NT], &x[base_g | P.roff[r]]);
-  cp_async_wait_all();
-  __syncthreads();
-
-  double ar[R], ai[R];
-  if (diag != nullptr) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const double d = __ldg(&diag[base_g | P.roff[r]]);
-      const double2 v = tile[tid + r * NT];
-      ar[r] = d * v.x;
-      ai[r] = d * v.y;
-    }
-  } else {
-#pragma unroll
-    for (int r = 0; r < R; ++r) ar[r] = ai[r] = 0.0;
-  }
-
-  for (int mi = 0; mi < P.nmasks; ++mi) {
-    const u32 lam = SMALL ? S.lam[mi] : __ldg(&P.lam[mi]);
-    const int base = tid ^ (int)(lam & (NT - 1));
-    const int hi_l = (int)(lam >> LOG_NT);
-    const int t0 = SMALL ? (int)S.t_re[mi] : __ldg(&P.t_re[mi]);
-    const int t1 = SMALL ? (int)S.t_im[mi] : __ldg(&P.t_im[mi]);
-    const int t2 = SMALL ? (int)S.t_end[mi] : __ldg(&P.t_end[mi]);
-#pragma unroll 1
-    for (int kind = 0; kind < 2; ++kind) {
-      const int ta = kind ? t1 : t0, tb = kind ? t2 : t1;
-      if (ta == tb) continue;
-      double d[R];
-      for (int t = ta; t < tb; ++t) {
-        const double c = SMALL ? S.cf[t] : __ldg(&P.cf[t]);
-        const i64 so = SMALL ? S.so[t] : __ldg(&P.so[t]);
-        const u32 sw = SMALL ? S.sw[t] : __ldg(&P.sw[t]);
-        const u32 rb = SMALL ? S.rb[t] : __ldg(&P.rb[t]);
-        const int p = (__popcll((unsigned long long)(so & outer_g)) ^ __popc(sw & (u32)tid)) & 1;
-        const u32 bits = rb ^ (u32)(-p);
-        const int chi = __double2hiint(c), clo = __double2loint(c);
-        if (t == ta) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) d[r] = flip_if(chi, clo, bits, r);
-        } else {
-#pragma unroll
-          for (int r = 0; r < R; ++r) d[r] += flip_if(chi, clo, bits, r);
-        }
-      }
-      if (kind == 0) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          if (d[r] != 0.0) {
-            const double2 v = tile[base + ((r ^ hi_l) << LOG_NT)];
-            ar[r] += d[r] * v.x;
-            ai[r] += d[r] * v.y;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          if (d[r] != 0.0) {
-            const double2 v = tile[base + ((r ^ hi_l) << LOG_NT)];
-            ar[r] -= d[r] * v.y;
-            ai[r] += d[r] * v.x;
-          }
-        }
-      }
-    }
-  }
-
-  if (P.accumulate) {
-    // reuse the tile buffer to fetch the previous pass's y with full memory-level parallelism
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < R; ++r) cp_async16(&tile[tid + r * NT], &y[base_g | P.roff[r]]);
-    cp_async_wait_all();
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const double2 old = tile[tid + r * NT];  // written by this thread's own copies
-      y[base_g | P.roff[r]] = make_double2(ar[r] + old.x, ai[r] + old.y);
-    }
-  } else {
-#pragma unroll
-    for (int r = 0; r < R; ++r) y[base_g | P.roff[r]] = make_double2(ar[r], ai[r]);
-  }
-}
+using namespace tiled;
 
 // Plain gather for masks no window can hold, and for index spaces smaller
 // than one tile.  Terms in global index coordinates (sw/rb unused).
@@ -332,8 +166,10 @@ struct Pass {
   SmallTables st{};
   bool small = false;
   int T = 0;
+  int R = 16;
   int peer_xor = 0;  // x is read from rank ^ peer_xor
   int nterms = 0;
+  int nmasks = 0;
   std::vector<void *> owned;
 };
 
@@ -353,6 +189,7 @@ struct TiledPlan {
   std::vector<Direct> directs;
   Direct all;  // every mask, for the row-local helpers (diag, norm)
   bool any_remote = false;
+  double cost = 0.0;  // estimated HBM sweeps per MatMult
   ~TiledPlan()
   {
     for (auto &ps : passes)
@@ -464,13 +301,15 @@ Direct make_direct(const std::vector<const NMask *> &masks, int nloc, int accumu
   return d;
 }
 
-Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &W, int T, int B, int nloc,
+Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &W, int T, int R, int B, int nloc,
                int accumulate)
 {
   Pass ps;
   ps.T = T;
-  const int log_nt = (T >= 10) ? T - 4 : 6;
-  const int R = (1 << T) >> log_nt;
+  ps.R = R;
+  int log_r = 0;
+  while ((1 << log_r) < R) ++log_r;
+  const int log_nt = T - log_r;
   const i64 lmask = ((i64)1 << nloc) - 1;
   i64 wbits = 0;
   for (int b : W) wbits |= (i64)1 << b;
@@ -481,24 +320,58 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
       if ((v >> W[b]) & 1) o |= 1u << b;
     return o;
   };
-
-  std::vector<u32> lam, sw, rb;
-  std::vector<int> t_re, t_im, t_end;
-  std::vector<i64> so;
-  std::vector<double> cf;
-  std::vector<const NTerm *> flat;
-  for (const NMask *nm : masks) lam.push_back(extract(nm->mask & lmask));
-  fill_term_ranges(masks, t_re, t_im, t_end, flat);
-  for (const NTerm *t : flat) {
-    const u32 w = extract(t->sign & lmask);
-    sw.push_back(w);
+  auto row_pattern = [&](u32 w) {
     u32 bits = 0;
     for (int r = 0; r < R; ++r)
       if (__builtin_parity((w >> log_nt) & (u32)r)) bits |= 1u << r;
-    rb.push_back(bits);
-    so.push_back(t->sign & ~wbits);  // outside the window, rank bits included
-    cf.push_back(t->coef);
+    return bits;
+  };
+
+  // groups: (mask, real|imaginary); inside a group the terms whose sign mask has no
+  // row bits come first
+  std::vector<u32> lam, sw, rb;
+  std::vector<u16> t0, t1, t2, pat;
+  std::vector<u8> kp;
+  std::vector<i64> so;
+  std::vector<double> cf;
+  for (const NMask *nm : masks) {
+    const u32 l = extract(nm->mask & lmask);
+    for (int kind = 0; kind < 2; ++kind) {
+      std::vector<const NTerm *> plain, rowdep;
+      for (const NTerm &t : nm->terms) {
+        if ((int)t.imag != kind) continue;
+        (((extract(t.sign & lmask) >> log_nt) == 0) ? plain : rowdep).push_back(&t);
+      }
+      if (plain.empty() && rowdep.empty()) continue;
+      lam.push_back(l);
+      t0.push_back((u16)sw.size());
+      for (const NTerm *t : plain) {
+        sw.push_back(extract(t->sign & lmask));
+        rb.push_back(0);
+        so.push_back(t->sign & ~wbits);  // outside the window, rank bits included
+        cf.push_back(t->coef);
+      }
+      t1.push_back((u16)sw.size());
+      bool one_pattern = true;
+      u32 first_pat = 0;
+      for (size_t k = 0; k < rowdep.size(); ++k) {
+        const u32 w = extract(rowdep[k]->sign & lmask);
+        const u32 bits = row_pattern(w);
+        if (k == 0) first_pat = bits;
+        else if (bits != first_pat) one_pattern = false;
+        sw.push_back(w);
+        rb.push_back(bits);
+        so.push_back(rowdep[k]->sign & ~wbits);
+        cf.push_back(rowdep[k]->coef);
+      }
+      t2.push_back((u16)sw.size());
+      const int path = rowdep.empty() ? PATH_SCALAR : (one_pattern ? PATH_TWO : PATH_GENERAL);
+      pat.push_back((u16)first_pat);
+      kp.push_back((u8)(kind | (path << 1)));
+    }
   }
+  DNM_REQUIRE(sw.size() < 65535, DNM_ERR_UNSUPPORTED, "too many terms in one pass (%zu)", sw.size());
+
   std::vector<i64> rowoff((size_t)1 << (T - B));
   for (size_t h = 0; h < rowoff.size(); ++h) {
     i64 off = 0;
@@ -506,16 +379,19 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
       if ((h >> (b - B)) & 1) off |= (i64)1 << W[b];
     rowoff[h] = off;
   }
-  ps.p.nmasks = (int)masks.size();
+  ps.p.ngroups = (int)lam.size();
+  ps.p.nterms = (int)sw.size();
   ps.p.B = B;
   ps.p.accumulate = accumulate;
   ps.p.n_outer = 0;
   for (int b = 0; b < nloc; ++b)
     if (!((wbits >> b) & 1)) ps.p.outer_pos[ps.p.n_outer++] = (unsigned char)b;
   ps.p.lam = up(lam, ps.owned);
-  ps.p.t_re = up(t_re, ps.owned);
-  ps.p.t_im = up(t_im, ps.owned);
-  ps.p.t_end = up(t_end, ps.owned);
+  ps.p.t0 = up(t0, ps.owned);
+  ps.p.t1 = up(t1, ps.owned);
+  ps.p.t2 = up(t2, ps.owned);
+  ps.p.pat = up(pat, ps.owned);
+  ps.p.kp = up(kp, ps.owned);
   ps.p.sw = up(sw, ps.owned);
   ps.p.rb = up(rb, ps.owned);
   ps.p.so = up(so, ps.owned);
@@ -524,14 +400,17 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
   ps.p.rank_bits = (i64)G.rank << nloc;
   for (int r = 0; r < 16; ++r) ps.p.roff[r] = 0;
   for (int r = 0; r < R; ++r) ps.p.roff[r] = rowoff[((size_t)r << log_nt) >> B];
-  ps.nterms = (int)flat.size();
-  ps.small = (int)masks.size() <= SMALL_MASKS && ps.nterms <= SMALL_TERMS;
+  ps.nmasks = (int)masks.size();
+  ps.nterms = (int)sw.size();
+  ps.small = ps.p.ngroups <= SMALL_GROUPS && ps.nterms <= SMALL_TERMS;
   if (ps.small) {
-    for (size_t k = 0; k < masks.size(); ++k) {
-      ps.st.lam[k] = lam[k];
-      ps.st.t_re[k] = (unsigned short)t_re[k];
-      ps.st.t_im[k] = (unsigned short)t_im[k];
-      ps.st.t_end[k] = (unsigned short)t_end[k];
+    for (int g = 0; g < ps.p.ngroups; ++g) {
+      ps.st.lam[g] = lam[g];
+      ps.st.pat[g] = pat[g];
+      ps.st.t0[g] = (u8)t0[g];
+      ps.st.t1[g] = (u8)t1[g];
+      ps.st.t2[g] = (u8)t2[g];
+      ps.st.kp[g] = kp[g];
     }
     for (int t = 0; t < ps.nterms; ++t) {
       ps.st.sw[t] = sw[t];
@@ -544,8 +423,8 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
 }
 
 // Greedy window cover of one partner group's masks.
-void plan_group(TiledPlan &plan, std::vector<const NMask *> remaining, int peer_xor, int T, int B, bool first_group,
-                int verbose)
+void plan_group(TiledPlan &plan, std::vector<const NMask *> remaining, int peer_xor, int T, int R, int B,
+                bool first_group, int verbose)
 {
   const int nloc = plan.nloc;
   const i64 lmask = ((i64)1 << nloc) - 1;
@@ -599,11 +478,11 @@ void plan_group(TiledPlan &plan, std::vector<const NMask *> remaining, int peer_
       if ((W >> b) & 1) Wpos.push_back(b);
     // masks are kept in ascending order inside a pass
     std::sort(chosen.begin(), chosen.end(), [](const NMask *a, const NMask *b) { return a->mask < b->mask; });
-    Pass ps = make_pass(chosen, Wpos, T, B, nloc, wrote ? 1 : 0);
+    Pass ps = make_pass(chosen, Wpos, T, R, B, nloc, wrote ? 1 : 0);
     ps.peer_xor = peer_xor;
     if (verbose)
       fprintf(stderr, "[dnm] pass %zu: peer^%d window=0x%llx masks=%d terms=%d %s\n", plan.passes.size(), peer_xor,
-              (unsigned long long)W, ps.p.nmasks, ps.nterms, wrote ? "accumulate" : "write");
+              (unsigned long long)W, ps.nmasks, ps.nterms, wrote ? "accumulate" : "write");
     plan.passes.push_back(std::move(ps));
     wrote = true;
     std::vector<const NMask *> rest;
@@ -623,26 +502,52 @@ struct PlanInputs {
   std::vector<NMask> masks;
 };
 
-template <int T, bool SMALL>
+template <int T, int R, bool SMALL>
 void launch_tiled_v(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
 {
   static bool attr_set = false;
   const size_t smem = sizeof(double2) << T;
   if (!attr_set) {
-    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled<T, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled<T, SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled<T, R, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled<T, R, SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
-  k_tiled<T, SMALL><<<(unsigned)ntiles, TileCfg<T>::NT, smem, G.stream>>>(ps.p, ps.st, x, y, diag);
+  k_tiled<T, R, SMALL><<<(unsigned)ntiles, TileCfg<T, R>::NT, smem, G.stream>>>(ps.p, ps.st, x, y, diag);
   count_launch();
   DNM_CHECK_CUDA(cudaGetLastError());
 }
 
-template <int T>
+template <int T, int R>
 void launch_tiled(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
 {
-  if (ps.small) launch_tiled_v<T, true>(ps, x, y, diag, ntiles);
-  else launch_tiled_v<T, false>(ps, x, y, diag, ntiles);
+  if (ps.small) launch_tiled_v<T, R, true>(ps, x, y, diag, ntiles);
+  else launch_tiled_v<T, R, false>(ps, x, y, diag, ntiles);
+}
+
+// rows per thread for a tile size: 16 by default (8 on request) where the CTA stays >= 64 threads
+int rows_for(int T, int want)
+{
+  if (T == 8) return 4;
+  if (T == 9) return 8;
+  return (want == 16) ? 16 : 8;  // 8 rows/thread (64 registers) doubles the resident warps; measured faster
+}
+
+void launch_pass(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
+{
+#define DNM_TILE_CASE(TT, RR) \
+  if (ps.T == TT && ps.R == RR) return launch_tiled<TT, RR>(ps, x, y, diag, ntiles);
+  DNM_TILE_CASE(8, 4)
+  DNM_TILE_CASE(9, 8)
+  DNM_TILE_CASE(10, 8)
+  DNM_TILE_CASE(10, 16)
+  DNM_TILE_CASE(11, 8)
+  DNM_TILE_CASE(11, 16)
+  DNM_TILE_CASE(12, 8)
+  DNM_TILE_CASE(12, 16)
+  DNM_TILE_CASE(13, 8)
+  DNM_TILE_CASE(13, 16)
+#undef DNM_TILE_CASE
+  DNM_REQUIRE(false, DNM_ERR_INTERNAL, "no tiled kernel for T=%d R=%d", ps.T, ps.R);
 }
 
 int direct_grid(i64 rows)
@@ -652,32 +557,29 @@ int direct_grid(i64 rows)
   return (int)std::max<i64>(1, std::min(want, cap));
 }
 
-TiledPlan *build_plan(dnm_mat_s *A)
+// One candidate plan for a fixed tile size T and run length 2^B.
+std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &masks, int T, int R, int B, int verbose)
 {
   std::unique_ptr<TiledPlan> plan(new TiledPlan());
   const int n = ilog2(A->M);
-  int p = ilog2(G.nranks);
+  const int p = ilog2(G.nranks);
   plan->n = n;
   plan->nloc = n - p;
   plan->use_diag = A->d_diag != nullptr;
   const int nloc = plan->nloc;
 
-  auto masks = std::make_shared<std::vector<NMask>>(normalise(A, n));
-  // NMask storage must outlive the planning only (everything is uploaded)
   std::vector<const NMask *> all;
-  for (const NMask &nm : *masks) all.push_back(&nm);
+  for (const NMask &nm : masks) all.push_back(&nm);
   plan->all = make_direct(all, nloc, 0);
 
   // group by partner rank
   std::map<int, std::vector<const NMask *>> groups;
   groups[0];  // group 0 always exists: its first pass writes y
-  for (const NMask &nm : *masks) {
+  for (const NMask &nm : masks) {
     if (plan->use_diag && nm.mask == 0) continue;  // served from the cached diagonal
     groups[(int)(nm.mask >> nloc)].push_back(&nm);
   }
 
-  int T = A->tile_bits ? A->tile_bits : 12;
-  T = std::min(T, nloc);
   if (T < 8) {
     // index space smaller than the smallest tile: plain gather only
     std::vector<const NMask *> g0 = groups[0];
@@ -691,18 +593,57 @@ TiledPlan *build_plan(dnm_mat_s *A)
       plan->any_remote = true;
     }
   } else {
-    int B = std::min(3, T - 1);
-    if (const char *e = getenv("DNM_TILE_RUN_BITS")) B = std::max(0, std::min(atoi(e), T - 1));
-    B = std::min(B, (T >= 10) ? T - 4 : 6);  // a thread's own index bits must cover the run bits
     bool first = true;
     for (auto &kv : groups) {
-      plan_group(*plan, kv.second, kv.first, T, B, first, A->verbose);
+      plan_group(*plan, kv.second, kv.first, T, R, B, first, verbose);
       first = false;
       if (kv.first != 0) plan->any_remote = true;
     }
   }
+  // cost in vector sweeps over HBM: a writing pass reads x and writes y (2), an
+  // accumulating pass also re-reads y (3); a direct gather re-reads x once per mask.
+  double cost = 0.0;
+  for (const Pass &ps : plan->passes) cost += ps.p.accumulate ? 3.0 : 2.0;
+  for (const Direct &d : plan->directs) cost += (d.p.accumulate ? 2.0 : 1.0) + d.p.nmasks;
+  // measured on B200: 128 KB tiles (one CTA per SM) and 64-byte runs are each a few % slower per sweep
+  if (T >= 13) cost *= 1.08;
+  if (B <= 2) cost *= 1.02;
+  plan->cost = cost;
+  return plan;
+}
+
+TiledPlan *build_plan(dnm_mat_s *A)
+{
+  const int n = ilog2(A->M);
+  const int nloc = n - ilog2(G.nranks);
+  const std::vector<NMask> masks = normalise(A, n);  // only needed while planning: plans own device copies
+
+  std::vector<std::pair<int, int>> candidates;  // (T, B)
+  const char *env_b = getenv("DNM_TILE_RUN_BITS");
+  // Measured on B200 (profiles/explore_r01.md): up to 2^28 rows per GPU 64 KB tiles (T=12) win;
+  // beyond that the passes over the highest bits touch hundreds of 2 MB pages per tile and
+  // 32 KB tiles (T=11, more CTAs per SM, one more pass) are faster.
+  std::vector<int> Ts = A->tile_bits ? std::vector<int>{A->tile_bits}
+                                     : (nloc >= 29 ? std::vector<int>{11} : std::vector<int>{12});
+  std::vector<int> Bs = env_b ? std::vector<int>{atoi(env_b)} : std::vector<int>{3, 2};
+  for (int T : Ts)
+    for (int B : Bs) {
+      T = std::min(T, nloc);
+      B = std::max(0, std::min(B, T - 1));
+      B = std::min(B, T - 4);  // a thread's own index bits (>= T-4 of them) must cover the run bits
+      if (std::find(candidates.begin(), candidates.end(), std::make_pair(T, B)) == candidates.end())
+        candidates.emplace_back(T, B);
+    }
+  std::unique_ptr<TiledPlan> best;
+  for (auto &tb : candidates) {
+    std::unique_ptr<TiledPlan> cand = plan_with(A, masks, tb.first, rows_for(tb.first, A->tile_rows), tb.second, 0);
+    if (A->verbose)
+      fprintf(stderr, "[dnm] plan T=%d B=%d: %zu passes + %zu direct, cost %.2f sweeps\n", tb.first, tb.second,
+              cand->passes.size(), cand->directs.size(), cand->cost);
+    if (!best || cand->cost < best->cost - 1e-9) best = std::move(cand);
+  }
   DNM_CHECK_CUDA(cudaStreamSynchronize(G.stream));
-  return plan.release();
+  return best.release();
 }
 
 void stream_barrier()
@@ -751,15 +692,7 @@ void tiled_mult(dnm_mat_s *A, dnm_vec_t xv, dnm_vec_t yv)
     const cplx *x = source(ps.peer_xor);
     const double *diag = (first && plan.use_diag) ? A->d_diag : nullptr;
     const i64 ntiles = nloc_rows >> ps.T;
-    switch (ps.T) {
-      case 8: launch_tiled<8>(ps, x, y, diag, ntiles); break;
-      case 9: launch_tiled<9>(ps, x, y, diag, ntiles); break;
-      case 10: launch_tiled<10>(ps, x, y, diag, ntiles); break;
-      case 11: launch_tiled<11>(ps, x, y, diag, ntiles); break;
-      case 12: launch_tiled<12>(ps, x, y, diag, ntiles); break;
-      case 13: launch_tiled<13>(ps, x, y, diag, ntiles); break;
-      default: DNM_REQUIRE(false, DNM_ERR_INTERNAL, "no tiled kernel for T=%d", ps.T);
-    }
+    launch_pass(ps, x, y, diag, ntiles);
     first = false;
     ++launches;
   }

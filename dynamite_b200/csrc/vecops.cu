@@ -80,6 +80,22 @@ __global__ void k_fill(cplx *__restrict__ v, int64_t n, cplx value)
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = value;
 }
 
+__global__ void k_random_fill(cplx *__restrict__ v, int64_t n, int64_t offset, uint64_t seed)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t z = (uint64_t)(i + offset) * 0x9E3779B97F4A7C15ull + seed * 0xD1B54A32D192ED03ull + 0x632BE59BD9B4E019ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    uint64_t z2 = z * 0x9E3779B97F4A7C15ull + 0x7F4A7C15ull;
+    z2 = (z2 ^ (z2 >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z2 ^= z2 >> 29;
+    const double a = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+    const double b = (double)(z2 >> 11) * (1.0 / 9007199254740992.0);
+    v[i] = make_double2(2.0 * a - 1.0, 2.0 * b - 1.0);
+  }
+}
+
 __global__ void k_scale(cplx *__restrict__ v, int64_t n, cplx a)
 {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -310,6 +326,14 @@ void vec_fill(cplx *v, int64_t n, cplx value)
 {
   if (n == 0) return;
   k_fill<<<stream_grid(n), TPB, 0, G.stream>>>(v, n, value);
+  count_launch();
+  DNM_CHECK_CUDA(cudaGetLastError());
+}
+
+void vec_random_fill(cplx *v, int64_t n, int64_t global_offset, uint64_t seed)
+{
+  if (n == 0) return;
+  k_random_fill<<<stream_grid(n), TPB, 0, G.stream>>>(v, n, global_offset, seed);
   count_launch();
   DNM_CHECK_CUDA(cudaGetLastError());
 }

@@ -18,6 +18,8 @@ struct VecList {
 int reduce_grid(int64_t n);
 
 void vec_fill(cplx *v, int64_t n, cplx value);
+// uniform [-1,1]^2 per entry from a counter-based hash of (global index, seed)
+void vec_random_fill(cplx *v, int64_t n, int64_t global_offset, uint64_t seed);
 void vec_copy(cplx *dst, const cplx *src, int64_t n);
 // v *= a  (a on host)
 void vec_scale(cplx *v, int64_t n, cplx a);

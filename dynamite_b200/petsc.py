@@ -171,6 +171,10 @@ class Vec:
         value = complex(value)
         check(_capi.lib().dnm_vec_set(self.handle, value.real, value.imag))
 
+    def setRandom(self, seed=0):
+        """device-side pseudo-random fill (synthetic data; not numpy's stream)"""
+        check(_capi.lib().dnm_vec_set_random(self.handle, int(seed)))
+
     def zeroEntries(self):
         self.set(0)
 

@@ -88,6 +88,9 @@ int dnm_timer_stop(float *milliseconds);
 int dnm_mem_info(int64_t *free_bytes, int64_t *total_bytes);
 /* number of kernels this library has launched since dnm_init / last reset */
 int64_t dnm_launch_count(int reset);
+/* page-locked host buffers for callers that stage vectors on the host */
+int dnm_host_alloc(int64_t bytes, void **out);
+int dnm_host_free(void *ptr);
 
 /* ---- multi-GPU (one process per GPU) ----------------------------------- */
 
@@ -138,6 +141,9 @@ int dnm_vec_get_host(dnm_vec_t v, int64_t offset, int64_t count, double *values)
 int dnm_vec_set_values(dnm_vec_t v, int64_t count, const int64_t *local_idx, const double *values, int add);
 int dnm_vec_get_values(dnm_vec_t v, int64_t count, const int64_t *local_idx, double *values);
 int dnm_vec_set(dnm_vec_t v, double re, double im);                 /* Vec.set */
+/* counter-based pseudo-random fill on the device (uniform in [-1,1] per component); synthetic
+ * benchmark inputs.  State.set_random keeps numpy's host stream for parity with the reference. */
+int dnm_vec_set_random(dnm_vec_t v, uint64_t seed);
 int dnm_vec_copy(dnm_vec_t src, dnm_vec_t dst);                     /* Vec.copy */
 int dnm_vec_scale(dnm_vec_t v, double re, double im);               /* Vec.scale */
 /* y = a*x + b*y                                                       Vec.axpby */
@@ -165,8 +171,9 @@ int dnm_mat_precompute_diagonal(dnm_mat_t A);
 /* MATOP_MULT  _backend/bcuda_template_2.cu:141-273.  y = A x, device resident,
  * asynchronous on the library stream. */
 int dnm_mat_mult(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y);
-/* Same product with HOST buffers: H2D of x, multiply, D2H of y, synchronous.
- * (what Mat.mult costs a caller whose Vec lives on the host) */
+/* Same product with HOST buffers: H2D of x, multiply, D2H of y, synchronous
+ * (what Mat.mult costs a caller whose Vec lives on the host).  The two device
+ * work vectors are created on first use and kept until dnm_mat_destroy. */
 int dnm_mat_mult_host(dnm_mat_t A, const double *x_host, double *y_host);
 /* MATOP_NORM (NORM_INFINITY only)  _backend/bcuda_template_2.cu:275-403; cached. */
 int dnm_mat_norm_inf(dnm_mat_t A, double *nrm);

@@ -69,6 +69,7 @@ def lib():
         L.orc_next_state.argtypes = [sp, C.c_int64, C.c_int64]
         L.orc_matmult.argtypes = [mp, sp, sp, C.c_int, _f64p, _f64p, _f64p]
         L.orc_precompute_diag.argtypes = [mp, sp, C.c_int, _f64p]
+        L.orc_precompute_diag_range.argtypes = [mp, sp, C.c_int64, C.c_int64, _f64p]
         L.orc_norm_inf.argtypes = [mp, sp, sp, C.c_int, _f64p]
         L.orc_check_conserves.argtypes = [mp, sp, sp, C.c_int, C.POINTER(C.c_int)]
         L.orc_rdm.argtypes = [_f64p, sp, C.c_int64, _i64p, C.c_int64, _f64p]
@@ -76,6 +77,7 @@ def lib():
         L.orc_compute_rcm.argtypes = [C.c_int64, _i64p, _i64p, _f64p, _i64p, C.c_int64,
                                       C.c_int64, C.c_int64]
         L.orc_matmult_fast.argtypes = [mp, sp, _f64p, _f64p, _f64p, C.c_int]
+        L.orc_matmult_fast_range.argtypes = [mp, sp, _f64p, _f64p, _f64p, C.c_int64, C.c_int64, C.c_int]
         _LIB = L
     return _LIB
 
@@ -218,11 +220,32 @@ def matmult_fast(msc, sub, x, diag=None, nthreads=1):
     return y, used
 
 
+def matmult_fast_range(msc, sub, x, y, blk_first, blk_last, diag=None, nthreads=1):
+    """Rows [2048*blk_first, 2048*blk_last) of y = A x with the fast path, in place in ``y``
+    (complex128, full length).  Used by bench.py to time a bounded sample of a big multiply."""
+    assert x.dtype == np.complex128 and y.dtype == np.complex128 and x.size == y.size == sub.dim
+    d = None
+    if diag is not None:
+        assert diag.dtype == np.float64
+        d = _fp(diag)
+    used = lib().orc_matmult_fast_range(C.byref(msc.c), C.byref(sub.c), d, _fp(x.view(np.float64)),
+                                        _fp(y.view(np.float64)), int(blk_first), int(blk_last), int(nthreads))
+    if used < 0:
+        raise ValueError('fast path needs Full/Parity, dim >= 2048 and a non-empty block range')
+    return used
+
+
 def precompute_diag(msc, sub, xparity=False):
     M = sub.dim // 2 if xparity else sub.dim
     d = np.empty(M, dtype=np.float64)
     rc = lib().orc_precompute_diag(C.byref(msc.c), C.byref(sub.c), int(xparity), _fp(d))
     return None if rc else d
+
+
+def precompute_diag_range(msc, sub, diag, row_first, row_last):
+    """fill diag[row_first:row_last] in place (float64, full length)"""
+    assert diag.dtype == np.float64
+    return lib().orc_precompute_diag_range(C.byref(msc.c), C.byref(sub.c), int(row_first), int(row_last), _fp(diag))
 
 
 def norm_inf(msc, left, right, xparity=False):

@@ -197,6 +197,23 @@ int orc_precompute_diag(const orc_msc *msc, const orc_subspace *sub, int xparity
   return 0;
 }
 
+/* same, rows [row_first, row_last) only (bench.py's bounded CPU sample) */
+int orc_precompute_diag_range(const orc_msc *msc, const orc_subspace *sub, int64_t row_first,
+                              int64_t row_last, double *diag)
+{
+  if (msc->nmasks == 0 || msc->masks[0] != 0) return 1;
+  for (int64_t row = row_first; row < row_last; ++row) {
+    int64_t state = orc_i2s(sub, row);
+    double v = 0;
+    for (int64_t t = 0; t < msc->mask_offsets[1]; ++t) {
+      double sign = 1 - 2 * par64(state & msc->signs[t]);
+      v += sign * real_coeff(msc, t);
+    }
+    diag[row] = v;
+  }
+  return 0;
+}
+
 /* bpetsc_template_2.c:906-981: max row sum of |element|, Kahan-summed */
 int orc_norm_inf(const orc_msc *msc, const orc_subspace *left, const orc_subspace *right,
                  int xparity, double *nrm)
@@ -451,14 +468,19 @@ static void *fast_worker(void *arg)
   return NULL;
 }
 
-int orc_matmult_fast(const orc_msc *msc, const orc_subspace *sub, const double *diag,
-                     const double *x_, double *y_, int nthreads)
+/* blocks [blk_first, blk_last) of 2048 rows only: the bounded sample bench.py times.
+ * y must still have room for the whole vector (only the sampled rows are written). */
+int orc_matmult_fast_range(const orc_msc *msc, const orc_subspace *sub, const double *diag,
+                           const double *x_, double *y_, int64_t blk_first, int64_t blk_last,
+                           int nthreads)
 {
   if (sub->type != ORC_FULL && sub->type != ORC_PARITY) return -1;
   const int64_t N = orc_dim(sub);
   if (N < BLK) return -1; /* reference falls back to the general path (:549) */
+  if (blk_last > N / BLK) blk_last = N / BLK;
+  if (blk_first < 0 || blk_first >= blk_last) return -1;
   if (nthreads < 1) nthreads = 1;
-  const int64_t nblk = N / BLK;
+  const int64_t nblk = blk_last - blk_first;
   if (nthreads > nblk) nthreads = (int)nblk;
 
   /* sign tables, :575-596 */
@@ -476,7 +498,7 @@ int orc_matmult_fast(const orc_msc *msc, const orc_subspace *sub, const double *
   fast_job *jobs = malloc(sizeof(fast_job) * nthreads);
   for (int t = 0; t < nthreads; ++t) {
     jobs[t] = (fast_job){msc, sub, diag, (const cplx *)x_, (cplx *)y_, tab_plain, tab_par,
-                         nblk * t / nthreads, nblk * (t + 1) / nthreads};
+                         blk_first + nblk * t / nthreads, blk_first + nblk * (t + 1) / nthreads};
     if (t > 0) pthread_create(&tid[t], NULL, fast_worker, &jobs[t]);
   }
   fast_worker(&jobs[0]);
@@ -486,4 +508,11 @@ int orc_matmult_fast(const orc_msc *msc, const orc_subspace *sub, const double *
   free(tab_plain);
   free(tab_par);
   return nthreads;
+}
+
+int orc_matmult_fast(const orc_msc *msc, const orc_subspace *sub, const double *diag,
+                     const double *x_, double *y_, int nthreads)
+{
+  if (sub->type != ORC_FULL && sub->type != ORC_PARITY) return -1;
+  return orc_matmult_fast_range(msc, sub, diag, x_, y_, 0, orc_dim(sub) / BLK, nthreads);
 }

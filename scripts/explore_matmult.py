@@ -49,13 +49,18 @@ for name, L in [(a.split(':')[0], int(a.split(':')[1])) for a in sys.argv[1:]]:
     for diag in (True, False):
         mat = build(H, sub, diag)
         model = mat.get_info('model_bytes')
-        for kern, tb, rb in [(1, 0, 3), (2, 12, 3), (2, 12, 2), (2, 12, 4), (2, 13, 3), (2, 13, 2), (2, 11, 3)]:
-            os.environ['DNM_TILE_RUN_BITS'] = str(rb)
+        for kern, tb, rb, rows in [(1, 0, 3, 0), (2, 12, 3, 16), (2, 12, 2, 16), (2, 12, 3, 8), (2, 12, 2, 8),
+                                   (2, 13, 3, 16), (2, 13, 3, 8), (2, 11, 3, 16), (2, 11, 3, 8), (2, 0, -1, 0)]:
+            if rb >= 0:
+                os.environ['DNM_TILE_RUN_BITS'] = str(rb)
+            else:
+                os.environ.pop('DNM_TILE_RUN_BITS', None)
             mat.set_option('kernel', kern)
             if kern == 2:
                 mat.set_option('tile_bits', tb)
+                mat.set_option('tile_rows', rows)
             ms = time_mult(mat, n)
-            print(f'{name} L={L} diag={diag} kernel={kern} T={tb} B={rb} passes={mat.get_info("passes"):.0f} '
+            print(f'{name} L={L} diag={diag} kernel={kern} T={tb} B={rb} R={rows} passes={mat.get_info("passes"):.0f} '
                   f'{ms:.3f} ms  model {model/ms/1e6:.0f} GB/s  compulsory {mat.get_info("compulsory_bytes")/ms/1e6:.0f} GB/s',
                   flush=True)
         mat.destroy()
