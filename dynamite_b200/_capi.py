@@ -60,6 +60,7 @@ _SIGNATURES = {
     'dnm_comm_init': (C.c_int, [C.c_int, C.c_int, C.c_char_p]),
     'dnm_comm_rank': (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'dnm_comm_barrier': (C.c_int, []),
+    'dnm_shard_plan': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, i64p, C.POINTER(C.c_int32), i64p]),
     'dnm_subspace_dim': (C.c_int, [_sp, i64p]),
     'dnm_subspace_s2i': (C.c_int, [_sp, C.c_int64, i64p, i64p]),
     'dnm_subspace_i2s': (C.c_int, [_sp, C.c_int64, i64p, i64p]),

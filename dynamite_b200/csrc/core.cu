@@ -286,6 +286,27 @@ extern "C" int dnm_comm_barrier(void)
   DNM_API_END
 }
 
+extern "C" int dnm_shard_plan(int n_index_bits, int nranks, int rank, int64_t nmasks, const int64_t *index_masks,
+                              int32_t *partner, int64_t *local_masks)
+{
+  DNM_API_BEGIN
+  DNM_REQUIRE(nranks >= 1 && (nranks & (nranks - 1)) == 0, DNM_ERR_ARG, "number of ranks must be a power of 2");
+  DNM_REQUIRE(rank >= 0 && rank < nranks, DNM_ERR_ARG, "bad rank");
+  DNM_REQUIRE(nmasks == 0 || (index_masks && partner && local_masks), DNM_ERR_ARG, "null pointer");
+  int p = 0;
+  while ((1 << p) < nranks) ++p;
+  DNM_REQUIRE(n_index_bits > p && n_index_bits <= 62, DNM_ERR_ARG, "index space too small for %d ranks", nranks);
+  const int nloc = n_index_bits - p;
+  const int64_t lmask = ((int64_t)1 << nloc) - 1;
+  for (int64_t k = 0; k < nmasks; ++k) {
+    DNM_REQUIRE(index_masks[k] >= 0 && (index_masks[k] >> n_index_bits) == 0, DNM_ERR_ARG,
+                "mask outside the index space");
+    partner[k] = rank ^ (int32_t)(index_masks[k] >> nloc);
+    local_masks[k] = index_masks[k] & lmask;
+  }
+  DNM_API_END
+}
+
 // ---- subspace index maps (host) ---------------------------------------------------
 
 namespace {

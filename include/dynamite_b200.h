@@ -106,6 +106,14 @@ int dnm_comm_rank(int *rank, int *nranks);
  * (handles travel over NCCL inside dnm_vec_create, which is then collective),
  * so MatMult kernels can load remote amplitudes over NVLink directly. */
 int dnm_comm_barrier(void);
+/* Host-only description of the sharding (no device needed; used by the multi-rank CPU tests).
+ * The index space has n_index_bits bits (L for Full, L-1 for Parity; one less under XParity) and
+ * rank r of nranks = 2^p owns the indices whose top p bits equal r.  For index-space flip mask
+ * index_masks[k], a row owned by `rank` gathers from rank partner[k] = rank ^ (mask >> n_local)
+ * at local index (i ^ local_masks[k]).  This is the reference's power-of-two block layout
+ * (_backend/bpetsc_template_2.c:768-797: proc_start_idx = proc_mask & (proc_me ^ m)). */
+int dnm_shard_plan(int n_index_bits, int nranks, int rank, int64_t nmasks, const int64_t *index_masks,
+                   int32_t *partner, int64_t *local_masks);
 
 /* ---- subspace index maps (host) ---------------------------------------- */
 

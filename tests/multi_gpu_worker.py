@@ -1,0 +1,103 @@
+"""Sharded-state checks, one process per GPU.  Launched by test_gpu_multi.py (or by hand):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29533 tests/multi_gpu_worker.py
+
+Every rank builds the same small problem, holds only its shard on its GPU, and compares its
+slice with the single-process oracle / scipy result.  Exit code 0 = all checks passed."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+
+def main():
+    import scipy.sparse.linalg
+    import torch.distributed as dist
+
+    import oracle
+    from dynamite_b200 import _capi, msc_tools
+    from dynamite_b200.computations import reduced_density_matrix
+    from dynamite_b200.hamiltonians import build_hamiltonian
+    from dynamite_b200.sharding import init_comm
+    from dynamite_b200.states import State
+    from dynamite_b200.subspaces import Full, Parity
+    from helpers import rand_state, rel_err
+
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    dist.init_process_group('gloo')
+    _capi.ensure_gpu(local_rank)
+    rank, world = init_comm(dist)
+    failures = []
+
+    def check(name, ok, detail=''):
+        if not ok:
+            failures.append(f'[rank {rank}] {name} {detail}')
+
+    def sharded_state(sub, full_vec):
+        s = State(subspace=sub)
+        a, b = s.vec.getOwnershipRange()
+        s.vec[a:b] = full_vec[a:b]
+        s.set_initialized()
+        return s, a, b
+
+    cases = [('MBL', 16, 'full'), ('long_range', 15, 'full'), ('heisenberg', 16, 'parity'), ('SYK', 8, 'parity')]
+    for name, L, kind in cases:
+        H = build_hamiltonian(name, L)
+        sub = Full(L=L) if kind == 'full' else Parity('even', L=L)
+        H.subspace = sub
+        spec = {'type': kind, 'L': L, 'space': 0}
+        osub = oracle.Subspace(spec)
+        H.reduce_msc()
+        masks, offs = msc_tools.mask_offsets(H.msc)
+        omsc = oracle.Msc(masks, offs, H.msc['signs'], H.msc['coeffs'])
+        xfull = rand_state(osub.dim, 7)
+        want = oracle.matmult(omsc, osub, osub, xfull)
+        for diag in (True, False):
+            H.precompute_diagonal = diag
+            x, a, b = sharded_state(sub, xfull)
+            y = H.dot(x)
+            check(f'matmult {name} L={L} {kind} diag={diag}', rel_err(y.vec[a:b], want[a:b]) < 1e-12,
+                  f'err={rel_err(y.vec[a:b], want[a:b]):.2e}')
+            nrm = H.infinity_norm()
+            check(f'norm {name}', abs(nrm - oracle.norm_inf(omsc, osub, osub)) < 1e-12 * nrm)
+            # global reductions
+            check('dot', abs(x.dot(y) - np.vdot(xfull, want)) < 1e-12)
+            check('norm2', abs(y.norm() - np.linalg.norm(want)) < 1e-12)
+        # Krylov consumers on the sharded state
+        if L <= 15 or name == 'heisenberg':
+            A = msc_tools.msc_to_numpy(H.msc, (osub.dim, osub.dim), osub.i2s, osub.s2i)
+            x, a, b = sharded_state(sub, xfull)
+            t = 3.0 / H.infinity_norm()
+            ev = H.evolve(x, t, tol=1e-12)
+            ref = scipy.sparse.linalg.expm_multiply(-1j * t * A, xfull)
+            check(f'evolve {name}', rel_err(ev.vec[a:b], ref[a:b]) < 1e-10, f'err={rel_err(ev.vec[a:b], ref[a:b]):.2e}')
+            evals, evecs = H.eigsolve(nev=3, getvecs=True, tol=1e-11)
+            w = scipy.sparse.linalg.eigsh(A, k=3, which='SA')[0]
+            check(f'eigsolve {name}', abs(evals[0] - w.min()) < 1e-9, f'{evals[:3]} vs {np.sort(w)}')
+            v0 = evecs[0]
+            Hv = H.dot(v0)
+            Hv.axpy(-evals[0], v0)
+            check(f'eigvec residual {name}', Hv.norm() < 1e-7, f'{Hv.norm():.2e}')
+        if kind == 'full':
+            x, a, b = sharded_state(sub, xfull)
+            for keep in ([0, 1, 2], [L - 1], [1, L - 2, L - 1], list(range(L - 5, L))):
+                got = reduced_density_matrix(x, keep)
+                check(f'rdm {keep}', np.allclose(got, oracle.rdm(xfull, osub, keep), atol=1e-12))
+        H.destroy_mat()
+
+    dist.barrier()
+    if failures:
+        print('\n'.join(failures), flush=True)
+        sys.exit(1)
+    if rank == 0:
+        print(f'multi-gpu worker ok on {world} ranks', flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
