@@ -308,7 +308,7 @@ extern "C" int dnm_mat_create(int64_t nmasks, const int64_t *masks, const int64_
     DNM_REQUIRE(tiled_supported(A.get()), DNM_ERR_UNSUPPORTED,
                 "multi-GPU sharding is implemented for Full->Full and same-sector Parity->Parity only "
                 "(other subspaces fit one GPU: run them as replicas)");
-    DNM_REQUIRE(A->M % G.nranks == 0 && (A->M / G.nranks) >= 4096, DNM_ERR_UNSUPPORTED,
+    DNM_REQUIRE(A->M % G.nranks == 0 && (A->M / G.nranks) >= 2, DNM_ERR_UNSUPPORTED,
                 "dimension %lld too small to shard over %d ranks", (long long)A->M, G.nranks);
   }
   A->local_M = A->M / G.nranks;

@@ -45,7 +45,7 @@ def main():
         s.set_initialized()
         return s, a, b
 
-    cases = [('MBL', 16, 'full'), ('long_range', 15, 'full'), ('heisenberg', 16, 'parity'), ('SYK', 8, 'parity')]
+    cases = [('MBL', 16, 'full'), ('long_range', 15, 'full'), ('heisenberg', 16, 'parity'), ('SYK', 9, 'parity')]
     for name, L, kind in cases:
         H = build_hamiltonian(name, L)
         sub = Full(L=L) if kind == 'full' else Parity('even', L=L)
