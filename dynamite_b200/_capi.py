@@ -120,7 +120,7 @@ def lib():
             raise ImportError(
                 f'{LIB_PATH} not found: build the CUDA extension first '
                 '(make -C dynamite_b200/csrc). dynamite_b200 has no CPU fallback.')
-        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        L = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res
