@@ -21,6 +21,7 @@
 // Only the small projected matrix crosses to the host, once per sub-step /
 // restart, for the dense expm / eigensolve.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -185,6 +186,28 @@ int64_t vector_budget(int64_t local_n)
   return std::max<int64_t>(0, ((int64_t)f - reserve) / (int64_t)(sizeof(cplx) * local_n));
 }
 
+// wall-clock phase accounting, printed when DNM_TRACE is set
+struct PhaseTimer {
+  const char *names[8] = {"setup", "issue", "wait", "dense", "combine", "teardown", "other", ""};
+  double acc[8] = {0};
+  std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+  bool on = getenv("DNM_TRACE") != nullptr;
+  void mark(int phase)
+  {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    acc[phase] += std::chrono::duration<double>(now - last).count();
+    last = now;
+  }
+  void report(const char *what)
+  {
+    if (!on) return;
+    fprintf(stderr, "[dnm trace] %s:", what);
+    for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.1fms", names[i], acc[i] * 1e3);
+    fprintf(stderr, "\n");
+  }
+};
+
 double round2(double t)
 {
   // round up to two significant digits, as expokit does with its step sizes
@@ -235,6 +258,7 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
   }
   const cd sgn = tscale / t_out;
 
+  PhaseTimer trace;
   Basis B;
   B.nloc = nloc;
   B.v.push_back(y);
@@ -285,6 +309,7 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
   double t_new = round2((1.0 / anorm) * std::pow((fact * tol) / (4.0 * beta * anorm), xm));
   double t_now = 0.0;
 
+  trace.mark(0);
   while (reason == 0) {
     ++its;
     if (!std::isfinite(t_new)) t_new = 1e300;
@@ -306,7 +331,9 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
     }
     DNM_CHECK_CUDA(cudaMemcpyAsync(h_H.data(), d_H, hbytes, cudaMemcpyDeviceToHost, G.stream));
     double avnorm2 = 0;
+    trace.mark(1);
     fetch_doubles(S.sq, &avnorm2, 1);  // also synchronises the copy above
+    trace.mark(2);
     const double avnorm = std::sqrt(avnorm2);
 
     // happy breakdown: the Krylov space became invariant after mb vectors
@@ -356,6 +383,7 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
       ++ireject;
     }
 
+    trace.mark(3);
     // w = V[:, 0:mx'] * (beta F), in place on v[0]
     const int ncomb = mb + std::max(0, k1 - 1);
     std::vector<double> coef(2 * ncomb);
@@ -375,6 +403,7 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
     vec_sqnorm_dev(B.ptr(0), nloc, G.d_scratch);
     fetch_doubles(G.d_scratch, &beta, 1);  // also makes `coef` safe to free
     beta = std::sqrt(beta);
+    trace.mark(4);
 
     t_now += t_step;
     if (t_now >= t_out * (1.0 - 1e-15)) {
@@ -386,6 +415,8 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
     }
   }
   DNM_CHECK_CUDA(cudaStreamSynchronize(G.stream));
+  trace.mark(6);
+  trace.report("evolve");
   if (reason_out) *reason_out = reason;
   if (its_out) *its_out = its;
   if (matmults_out) *matmults_out = matmults;
