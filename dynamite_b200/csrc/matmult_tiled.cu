@@ -170,6 +170,7 @@ struct Pass {
   int peer_xor = 0;  // x is read from rank ^ peer_xor
   int nterms = 0;
   int nmasks = 0;
+  i64 wbits = 0;     // window bit positions
   std::vector<void *> owned;
 };
 
@@ -181,11 +182,22 @@ struct Direct {
 
 }  // namespace
 
+// A launch unit: one pass, or several consecutive passes fused through the L2 (k_tiled_fused)
+struct Unit {
+  std::vector<int> passes;  // indices into TiledPlan::passes
+  bool fused = false;
+  FusedParams fp{};
+  int *d_sync = nullptr;    // done counters followed by the ticket (8-byte aligned at the end)
+  size_t sync_bytes = 0;
+  int grid = 0;
+};
+
 struct TiledPlan {
   int n = 0;      // index bits (global)
   int nloc = 0;   // index bits on this rank
   bool use_diag = false;
   std::vector<Pass> passes;
+  std::vector<Unit> units;
   std::vector<Direct> directs;
   Direct all;  // every mask, for the row-local helpers (diag, norm)
   bool any_remote = false;
@@ -197,6 +209,8 @@ struct TiledPlan {
     for (auto &d : directs)
       for (void *q : d.owned) cudaFree(q);
     for (void *q : all.owned) cudaFree(q);
+    for (auto &u : units)
+      if (u.d_sync) cudaFree(u.d_sync);
   }
 };
 
@@ -402,6 +416,7 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
   for (int r = 0; r < R; ++r) ps.p.roff[r] = rowoff[((size_t)r << log_nt) >> B];
   ps.nmasks = (int)masks.size();
   ps.nterms = (int)sw.size();
+  ps.wbits = wbits;
   ps.small = ps.p.ngroups <= SMALL_GROUPS && ps.nterms <= SMALL_TERMS;
   if (ps.small) {
     for (int g = 0; g < ps.p.ngroups; ++g) {
@@ -557,6 +572,113 @@ int direct_grid(i64 rows)
   return (int)std::max<i64>(1, std::min(want, cap));
 }
 
+template <int T, int R>
+void launch_fused_tr(const Unit &u, const cplx *x, cplx *y, const double *diag)
+{
+  static int occ = 0;
+  const size_t smem = sizeof(double2) << T;
+  if (!occ) {
+    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_fused<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_fused<T, R>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    DNM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tiled_fused<T, R>, TileCfg<T, R>::NT, smem));
+    if (occ < 1) occ = 1;
+  }
+  DNM_CHECK_CUDA(cudaMemsetAsync(u.d_sync, 0, u.sync_bytes, G.stream));
+  const unsigned long long cap = (unsigned long long)G.sm_count * occ;
+  const unsigned grid = (unsigned)std::min<unsigned long long>(cap, u.fp.nitems);
+  k_tiled_fused<T, R><<<grid, TileCfg<T, R>::NT, smem, G.stream>>>(u.fp, x, y, diag);
+  count_launch();
+  DNM_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_fused(const Unit &u, int T, int R, const cplx *x, cplx *y, const double *diag)
+{
+#define DNM_FUSE_CASE(TT, RR) \
+  if (T == TT && R == RR) return launch_fused_tr<TT, RR>(u, x, y, diag);
+  DNM_FUSE_CASE(8, 4)
+  DNM_FUSE_CASE(9, 8)
+  DNM_FUSE_CASE(10, 8)
+  DNM_FUSE_CASE(10, 16)
+  DNM_FUSE_CASE(11, 8)
+  DNM_FUSE_CASE(11, 16)
+  DNM_FUSE_CASE(12, 8)
+  DNM_FUSE_CASE(12, 16)
+  DNM_FUSE_CASE(13, 8)
+  DNM_FUSE_CASE(13, 16)
+#undef DNM_FUSE_CASE
+  DNM_REQUIRE(false, DNM_ERR_INTERNAL, "no fused kernel for T=%d R=%d", T, R);
+}
+
+// Group consecutive local passes whose windows together span few enough bits for their
+// chunk (x and y) to stay in the L2 between passes.
+void build_units(TiledPlan &plan, int verbose)
+{
+  // Off by default: measured on B200 (profiles/r01_fusion_experiment.md) the fused persistent kernel
+  // halves DRAM traffic but is dependency/latency bound and slower than the per-pass kernels.
+  // DNM_FUSE_BITS=18 enables it (2^18 amplitudes = 4 MiB of x + 4 MiB of y per chunk).
+  int fuse_bits = 0;
+  int lag = 2;
+  if (const char *e = getenv("DNM_FUSE_BITS")) fuse_bits = atoi(e);
+  if (const char *e = getenv("DNM_FUSE_LAG")) lag = std::max(1, atoi(e));
+  const int nloc = plan.nloc;
+  size_t i = 0;
+  while (i < plan.passes.size()) {
+    Unit u;
+    u.passes.push_back((int)i);
+    const Pass &first = plan.passes[i];
+    i64 U = first.wbits;
+    size_t j = i + 1;
+    if (fuse_bits > 0 && first.small && first.peer_xor == 0) {
+      while (j < plan.passes.size() && (int)u.passes.size() < MAX_FUSED_PASSES) {
+        const Pass &nx = plan.passes[j];
+        if (!nx.small || nx.peer_xor != 0 || nx.T != first.T || nx.R != first.R) break;
+        if (popc64(U | nx.wbits) > std::min(fuse_bits, nloc)) break;
+        U |= nx.wbits;
+        u.passes.push_back((int)j);
+        ++j;
+      }
+    }
+    // local small passes always run in the persistent kernel (it prefetches through the L2),
+    // fused when more than one pass shares a chunk
+    if (u.passes.size() > 1 || (fuse_bits > 0 && first.small && first.peer_xor == 0 && getenv("DNM_PERSISTENT"))) {
+      const int ubits = popc64(U);
+      u.fused = true;
+      FusedParams &fp = u.fp;
+      fp.npasses = (int)u.passes.size();
+      fp.lag = lag;
+      fp.log_tiles = ubits - first.T;
+      fp.nchunks = (long long)1 << (nloc - ubits);
+      fp.nitems = (unsigned long long)(fp.nchunks + (long long)(fp.npasses - 1) * lag) * fp.npasses << fp.log_tiles;
+      fp.diag_pass = -1;
+      for (int k = 0; k < fp.npasses; ++k) {
+        const Pass &ps = plan.passes[u.passes[k]];
+        fp.p[k] = ps.p;
+        fp.s[k] = ps.st;
+        // tile id = (tile within chunk) | (chunk << log_tiles): first the chunk-internal positions
+        // outside this pass's window, then the positions outside the chunk (same order for every pass)
+        int pos = 0;
+        for (int b = 0; b < nloc; ++b)
+          if (((U >> b) & 1) && !((ps.wbits >> b) & 1)) fp.p[k].outer_pos[pos++] = (unsigned char)b;
+        for (int b = 0; b < nloc; ++b)
+          if (!((U >> b) & 1)) fp.p[k].outer_pos[pos++] = (unsigned char)b;
+        fp.p[k].n_outer = pos;
+        if (plan.use_diag && u.passes[k] == 0) fp.diag_pass = k;
+      }
+      const size_t nflags = (size_t)(fp.npasses - 1) * (size_t)fp.nchunks;
+      const size_t flag_bytes = (nflags * sizeof(int) + 7) / 8 * 8;
+      u.sync_bytes = flag_bytes + sizeof(unsigned long long);
+      DNM_CHECK_CUDA(cudaMalloc(&u.d_sync, u.sync_bytes));
+      fp.done = u.d_sync;
+      fp.ticket = (unsigned long long *)((char *)u.d_sync + flag_bytes);
+      if (verbose)
+        fprintf(stderr, "[dnm] fused unit: passes %d..%d, chunk bits %d (%lld chunks, %d tiles each), lag %d\n",
+                u.passes.front(), u.passes.back(), ubits, fp.nchunks, 1 << fp.log_tiles, lag);
+    }
+    plan.units.push_back(std::move(u));
+    i = j;
+  }
+}
+
 // One candidate plan for a fixed tile size T and run length 2^B.
 std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &masks, int T, int R, int B, int verbose)
 {
@@ -602,8 +724,12 @@ std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &mas
   }
   // cost in vector sweeps over HBM: a writing pass reads x and writes y (2), an
   // accumulating pass also re-reads y (3); a direct gather re-reads x once per mask.
+  build_units(*plan, verbose);
   double cost = 0.0;
-  for (const Pass &ps : plan->passes) cost += ps.p.accumulate ? 3.0 : 2.0;
+  for (const Unit &u : plan->units) {
+    // a fused unit reads x once and writes y once (plus the old y when it accumulates)
+    cost += plan->passes[u.passes.front()].p.accumulate ? 3.0 : 2.0;
+  }
   for (const Direct &d : plan->directs) cost += (d.p.accumulate ? 2.0 : 1.0) + d.p.nmasks;
   // measured on B200: 128 KB tiles (one CTA per SM) and 64-byte runs are each a few % slower per sweep
   if (T >= 13) cost *= 1.08;
@@ -636,7 +762,7 @@ TiledPlan *build_plan(dnm_mat_s *A)
     }
   std::unique_ptr<TiledPlan> best;
   for (auto &tb : candidates) {
-    std::unique_ptr<TiledPlan> cand = plan_with(A, masks, tb.first, rows_for(tb.first, A->tile_rows), tb.second, 0);
+    std::unique_ptr<TiledPlan> cand = plan_with(A, masks, tb.first, rows_for(tb.first, A->tile_rows), tb.second, A->verbose);
     if (A->verbose)
       fprintf(stderr, "[dnm] plan T=%d B=%d: %zu passes + %zu direct, cost %.2f sweeps\n", tb.first, tb.second,
               cand->passes.size(), cand->directs.size(), cand->cost);
@@ -688,11 +814,15 @@ void tiled_mult(dnm_mat_s *A, dnm_vec_t xv, dnm_vec_t yv)
   if (plan.any_remote) stream_barrier();  // every rank's x is complete before anyone pulls from it
 
   bool first = true;
-  for (const Pass &ps : plan.passes) {
+  for (const Unit &u : plan.units) {
+    const Pass &ps = plan.passes[u.passes.front()];
     const cplx *x = source(ps.peer_xor);
     const double *diag = (first && plan.use_diag) ? A->d_diag : nullptr;
-    const i64 ntiles = nloc_rows >> ps.T;
-    launch_pass(ps, x, y, diag, ntiles);
+    if (u.fused) {
+      launch_fused(u, ps.T, ps.R, x, y, plan.use_diag ? A->d_diag : nullptr);
+    } else {
+      launch_pass(ps, x, y, diag, nloc_rows >> ps.T);
+    }
     first = false;
     ++launches;
   }

@@ -98,47 +98,78 @@ __device__ __forceinline__ void cp_async_wait_all()
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-// acc[r] += (IMAG ? i*d : d) * tile[row r ^ lam]   for the rows selected by `rows` (uniform bit mask)
-template <int R, int LOG_NT, bool IMAG, bool ALL>
-__device__ __forceinline__ void gather_rows(double (&ar)[R], double (&ai)[R], const double2 *tile, int base, int hi_l,
-                                            double d, u32 rows)
+// acc[r] += (IMAG ? i*d_r : d_r) * tile[(r ^ HI) rows, column `base`]: HI is a template
+// parameter so every LDS has an immediate offset and there is no per-row address arithmetic.
+template <int R, int LOG_NT, int HI, bool IMAG, bool SCALAR>
+__device__ __forceinline__ void gather_fixed(double (&ar)[R], double (&ai)[R], const double2 *col, double d0,
+                                             const double (&d)[R])
 {
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    if (ALL || ((rows >> r) & 1u)) {
-      const double2 v = tile[base + ((r ^ hi_l) << LOG_NT)];
-      if (IMAG) {
-        ar[r] -= d * v.y;
-        ai[r] += d * v.x;
-      } else {
-        ar[r] += d * v.x;
-        ai[r] += d * v.y;
-      }
+    const double2 v = col[(r ^ HI) << LOG_NT];
+    const double c = SCALAR ? d0 : d[r];
+    if (IMAG) {
+      ar[r] -= c * v.y;
+      ai[r] += c * v.x;
+    } else {
+      ar[r] += c * v.x;
+      ai[r] += c * v.y;
     }
   }
 }
 
+template <int R, int LOG_NT, bool IMAG, bool SCALAR>
+__device__ __forceinline__ void gather_switch(double (&ar)[R], double (&ai)[R], const double2 *col, int hi_l, double d0,
+                                              const double (&d)[R])
+{
+#define DNM_HI_CASE(H) \
+  case H:               \
+    if (H < R) gather_fixed<R, LOG_NT, (H < R ? H : 0), IMAG, SCALAR>(ar, ai, col, d0, d); \
+    break;
+  switch (hi_l) {
+    DNM_HI_CASE(0) DNM_HI_CASE(1) DNM_HI_CASE(2) DNM_HI_CASE(3) DNM_HI_CASE(4) DNM_HI_CASE(5) DNM_HI_CASE(6)
+    DNM_HI_CASE(7) DNM_HI_CASE(8) DNM_HI_CASE(9) DNM_HI_CASE(10) DNM_HI_CASE(11) DNM_HI_CASE(12) DNM_HI_CASE(13)
+    DNM_HI_CASE(14) DNM_HI_CASE(15)
+    default: break;
+  }
+#undef DNM_HI_CASE
+}
+
+// One tile of one pass.  `tile` is the CTA's 2^T-entry shared buffer, `csign` its per-term scratch.
+// global index bits fixed by the tile number (the positions outside the window)
+__device__ __forceinline__ i64 tile_outer_bits(const PassParams &P, unsigned long long tile_id)
+{
+  i64 g = 0;
+  for (int k = 0; k < P.n_outer; ++k) g |= (i64)((tile_id >> k) & 1ull) << P.outer_pos[k];
+  return g;
+}
+
+// this thread's part of the address: its rows differ only by the uniform P.roff[r]
+__device__ __forceinline__ i64 thread_base(const PassParams &P, i64 outer)
+{
+  const int tid = threadIdx.x;
+  return outer | __ldg(&P.rowoff[tid >> P.B]) | (i64)(tid & ((1 << P.B) - 1));
+}
+
+// pull the 128-byte lines of a tile of `v` towards the L2 (one request per line)
+template <int R>
+__device__ __forceinline__ void prefetch_tile_l2(const PassParams &P, const cplx *v, i64 base_g)
+{
+  if ((threadIdx.x & 7) == 0 || P.B < 3) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(v + (base_g | P.roff[r])));
+  }
+}
+
 template <int T, int R, bool SMALL>
-__global__ void __launch_bounds__(TileCfg<T, R>::NT, TileCfg<T, R>::MINB)
-    k_tiled(const __grid_constant__ PassParams P, const __grid_constant__ SmallTables S,
-            const cplx *__restrict__ x, cplx *__restrict__ y, const double *__restrict__ diag)
+__device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables &S, i64 outer, i64 base_g,
+                                          const cplx *__restrict__ x, cplx *__restrict__ y,
+                                          const double *__restrict__ diag, double2 *tile, double *csign)
 {
   constexpr int NT = TileCfg<T, R>::NT;
   constexpr int LOG_NT = TileCfg<T, R>::LOG_NT;
-  constexpr u32 ALLROWS = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
-  extern __shared__ double2 tile[];
-  __shared__ double csign[SMALL ? SMALL_TERMS : 1];
   const int tid = threadIdx.x;
-
-  // scatter the tile number into the bit positions outside the window
-  i64 base_g = 0;
-  {
-    const unsigned long long b = blockIdx.x;
-    for (int k = 0; k < P.n_outer; ++k) base_g |= (i64)((b >> k) & 1ull) << P.outer_pos[k];
-  }
-  const i64 outer_g = base_g | P.rank_bits;  // sign-relevant bits shared by the whole tile
-  // this thread's part of the address: its rows differ only by the uniform P.roff[r]
-  base_g |= __ldg(&P.rowoff[tid >> P.B]) | (i64)(tid & ((1 << P.B) - 1));
+  const i64 outer_g = outer | P.rank_bits;  // sign-relevant bits shared by the whole tile
 
   // stage the tile: runs of 2^B contiguous amplitudes, asynchronous 16-byte copies
 #pragma unroll
@@ -187,47 +218,41 @@ __global__ void __launch_bounds__(TileCfg<T, R>::NT, TileCfg<T, R>::MINB)
     double c0 = 0.0;  // terms without r bits: one scalar per thread
     for (int t = t0; t < t1; ++t) c0 += term(t);
 
+    const double2 *col = tile + base;
     if (path == PATH_SCALAR) {
       if (c0 != 0.0) {
-        if (imag) gather_rows<R, LOG_NT, true, true>(ar, ai, tile, base, hi_l, c0, ALLROWS);
-        else gather_rows<R, LOG_NT, false, true>(ar, ai, tile, base, hi_l, c0, ALLROWS);
-      }
-    } else if (path == PATH_TWO) {
-      double ch = 0.0;  // terms sharing the single r pattern `pat`
-      for (int t = t1; t < t2; ++t) ch += term(t);
-      const u32 pat = SMALL ? (u32)S.pat[g] : (u32)__ldg(&P.pat[g]);
-      const double dp = c0 + ch, dm = c0 - ch;
-      if (dp != 0.0) {
-        if (imag) gather_rows<R, LOG_NT, true, false>(ar, ai, tile, base, hi_l, dp, ~pat & ALLROWS);
-        else gather_rows<R, LOG_NT, false, false>(ar, ai, tile, base, hi_l, dp, ~pat & ALLROWS);
-      }
-      if (dm != 0.0) {
-        if (imag) gather_rows<R, LOG_NT, true, false>(ar, ai, tile, base, hi_l, dm, pat);
-        else gather_rows<R, LOG_NT, false, false>(ar, ai, tile, base, hi_l, dm, pat);
+        const double none[R] = {};
+        if (imag) gather_switch<R, LOG_NT, true, true>(ar, ai, col, hi_l, c0, none);
+        else gather_switch<R, LOG_NT, false, true>(ar, ai, col, hi_l, c0, none);
       }
     } else {
       double d[R];
+      bool any;
+      if (path == PATH_TWO) {
+        double ch = 0.0;  // terms sharing the single r pattern `pat`
+        for (int t = t1; t < t2; ++t) ch += term(t);
+        const u32 pat = SMALL ? (u32)S.pat[g] : (u32)__ldg(&P.pat[g]);
+        const double dp = c0 + ch, dm = c0 - ch;
 #pragma unroll
-      for (int r = 0; r < R; ++r) d[r] = c0;
-      for (int t = t1; t < t2; ++t) {
-        const double c = term(t);
-        const u32 bits = SMALL ? S.rb[t] : __ldg(&P.rb[t]);
-        const int chi = __double2hiint(c), clo = __double2loint(c);
+        for (int r = 0; r < R; ++r) d[r] = ((pat >> r) & 1u) ? dm : dp;
+        any = (dp != 0.0) || (dm != 0.0);
+      } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r) d[r] += flip_if(chi, clo, bits, r);
-      }
+        for (int r = 0; r < R; ++r) d[r] = c0;
+        for (int t = t1; t < t2; ++t) {
+          const double c = term(t);
+          const u32 bits = SMALL ? S.rb[t] : __ldg(&P.rb[t]);
+          const int chi = __double2hiint(c), clo = __double2loint(c);
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (d[r] != 0.0) {
-          const double2 v = tile[base + ((r ^ hi_l) << LOG_NT)];
-          if (imag) {
-            ar[r] -= d[r] * v.y;
-            ai[r] += d[r] * v.x;
-          } else {
-            ar[r] += d[r] * v.x;
-            ai[r] += d[r] * v.y;
-          }
+          for (int r = 0; r < R; ++r) d[r] += flip_if(chi, clo, bits, r);
         }
+        any = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) any = any || (d[r] != 0.0);
+      }
+      if (any) {
+        if (imag) gather_switch<R, LOG_NT, true, false>(ar, ai, col, hi_l, 0.0, d);
+        else gather_switch<R, LOG_NT, false, false>(ar, ai, col, hi_l, 0.0, d);
       }
     }
   }
@@ -246,6 +271,112 @@ __global__ void __launch_bounds__(TileCfg<T, R>::NT, TileCfg<T, R>::MINB)
   } else {
 #pragma unroll
     for (int r = 0; r < R; ++r) y[base_g | P.roff[r]] = make_double2(ar[r], ai[r]);
+  }
+}
+
+// one pass, one tile per CTA
+template <int T, int R, bool SMALL>
+__global__ void __launch_bounds__(TileCfg<T, R>::NT, TileCfg<T, R>::MINB)
+    k_tiled(const __grid_constant__ PassParams P, const __grid_constant__ SmallTables S,
+            const cplx *__restrict__ x, cplx *__restrict__ y, const double *__restrict__ diag)
+{
+  extern __shared__ double2 tile[];
+  __shared__ double csign[SMALL ? SMALL_TERMS : 1];
+  const i64 outer = tile_outer_bits(P, blockIdx.x);
+  tile_body<T, R, SMALL>(P, S, outer, thread_base(P, outer), x, y, diag, tile, csign);
+}
+
+// ---- L2-fused passes ---------------------------------------------------------------------
+// Consecutive passes whose windows together span only u index bits work on CHUNKS of 2^u
+// amplitudes (all indices that agree outside those u bits).  If pass k+1 of a chunk runs soon
+// after pass k of the same chunk, its x tile and the y it read-modify-writes are still in the
+// 126 MB L2, so the pair costs one x read and one y write of DRAM traffic instead of two reads,
+// a y re-read and two writes.  One persistent kernel walks the (chunk, pass, tile) items in an
+// order where pass k of chunk c is issued `lag` chunks after pass k-1 of chunk c; a CTA takes
+// the next item with an atomic ticket, waits on a per-(pass, chunk) completion counter when
+// the item is not the first pass, and bumps the counter when it is done.  Tickets are handed
+// out in dependency order, so the scheme cannot deadlock whatever the residency.
+constexpr int MAX_FUSED_PASSES = 4;
+
+struct FusedParams {
+  PassParams p[MAX_FUSED_PASSES];
+  SmallTables s[MAX_FUSED_PASSES];
+  int npasses;
+  int lag;                 // chunks between consecutive passes of the same chunk
+  int log_tiles;           // log2(tiles per chunk per pass)
+  long long nchunks;
+  unsigned long long nitems;
+  int *done;               // [(npasses-1) * nchunks] tiles finished per (pass, chunk)
+  unsigned long long *ticket;
+  int diag_pass;           // pass that applies the cached diagonal (-1: none)
+};
+
+template <int T, int R>
+__global__ void __launch_bounds__(TileCfg<T, R>::NT, TileCfg<T, R>::MINB)
+    k_tiled_fused(const __grid_constant__ FusedParams F, const cplx *__restrict__ x, cplx *__restrict__ y,
+                  const double *__restrict__ diag)
+{
+  extern __shared__ double2 tile[];
+  __shared__ double csign[SMALL_TERMS];
+  __shared__ unsigned long long s_item;
+  const int tiles = 1 << F.log_tiles;
+  const unsigned long long per_step = (unsigned long long)F.npasses * tiles;
+
+  // decode an item; returns false for the ramp-up / ramp-down slots and past the end
+  auto decode = [&](unsigned long long item, int &k, long long &c, unsigned long long &tile_id) -> bool {
+    if (item >= F.nitems) return false;
+    const long long step = (long long)(item / per_step);
+    const int rem = (int)(item % per_step);
+    k = rem >> F.log_tiles;
+    c = step - (long long)k * F.lag;
+    tile_id = (unsigned long long)(rem & (tiles - 1)) | ((unsigned long long)c << F.log_tiles);
+    return c >= 0 && c < F.nchunks;
+  };
+
+  if (threadIdx.x == 0) s_item = atomicAdd(F.ticket, 1ull);
+  __syncthreads();
+  unsigned long long item = s_item;
+  while (item < F.nitems) {
+    __syncthreads();  // everyone has read s_item; the previous item's smem reads are finished
+    if (threadIdx.x == 0) s_item = atomicAdd(F.ticket, 1ull);  // the item after this one
+    int k;
+    long long c;
+    unsigned long long tile_id;
+    const bool live = decode(item, k, c, tile_id);
+    if (live) {
+      const PassParams &P = F.p[k];
+      const i64 outer = tile_outer_bits(P, tile_id);
+      const i64 base_g = thread_base(P, outer);
+      // the old y of this tile is needed only at the end: start pulling it into the L2 now
+      if (P.accumulate) prefetch_tile_l2<R>(P, y, base_g);
+      if (k > 0) {
+        if (threadIdx.x == 0) {
+          const volatile int *flag = F.done + (size_t)(k - 1) * F.nchunks + c;
+          while (*flag < tiles) __nanosleep(64);
+          __threadfence();
+        }
+      }
+      __syncthreads();  // dependency satisfied; s_item (next) is published
+      {
+        // warm the L2 with the next item's x tile while this one is being computed
+        int kn;
+        long long cn;
+        unsigned long long tn;
+        if (decode(s_item, kn, cn, tn)) {
+          const PassParams &Pn = F.p[kn];
+          prefetch_tile_l2<R>(Pn, x, thread_base(Pn, tile_outer_bits(Pn, tn)));
+        }
+      }
+      tile_body<T, R, true>(P, F.s[k], outer, base_g, x, y, (k == F.diag_pass) ? diag : nullptr, tile, csign);
+      if (k + 1 < F.npasses) {
+        __threadfence();  // this thread's y stores are visible device-wide
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(F.done + (size_t)k * F.nchunks + c, 1);
+      }
+    } else {
+      __syncthreads();
+    }
+    item = s_item;
   }
 }
 

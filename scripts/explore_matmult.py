@@ -46,21 +46,24 @@ for name, L in [(a.split(':')[0], int(a.split(':')[1])) for a in sys.argv[1:]]:
     H = build_hamiltonian(name, L)
     sub = Full(L=L)
     n = 1 << L
-    for diag in (True, False):
+    for diag in (True,):
         mat = build(H, sub, diag)
         model = mat.get_info('model_bytes')
-        for kern, tb, rb, rows in [(1, 0, 3, 0), (2, 12, 3, 16), (2, 12, 2, 16), (2, 12, 3, 8), (2, 12, 2, 8),
-                                   (2, 13, 3, 16), (2, 13, 3, 8), (2, 11, 3, 16), (2, 11, 3, 8), (2, 0, -1, 0)]:
+        for kern, tb, rb, rows, fuse, lag in [(2, 11, 3, 8, 0, 2), (2, 11, 3, 8, 18, 2), (2, 11, 3, 8, 18, 1), (2, 11, 3, 8, 18, 4),
+                                              (2, 11, 3, 8, 20, 2), (2, 11, 3, 8, 16, 2), (2, 12, 3, 8, 18, 2), (2, 12, 3, 8, 20, 2),
+                                              (2, 12, 2, 8, 20, 2), (2, 11, 2, 8, 18, 2), (2, 11, 3, 16, 18, 2), (2, 0, -1, 0, 18, 2)]:
             if rb >= 0:
                 os.environ['DNM_TILE_RUN_BITS'] = str(rb)
             else:
                 os.environ.pop('DNM_TILE_RUN_BITS', None)
+            os.environ['DNM_FUSE_BITS'] = str(fuse)
+            os.environ['DNM_FUSE_LAG'] = str(lag)
             mat.set_option('kernel', kern)
             if kern == 2:
                 mat.set_option('tile_bits', tb)
                 mat.set_option('tile_rows', rows)
             ms = time_mult(mat, n)
-            print(f'{name} L={L} diag={diag} kernel={kern} T={tb} B={rb} R={rows} passes={mat.get_info("passes"):.0f} '
+            print(f'{name} L={L} diag={diag} T={tb} B={rb} R={rows} fuse={fuse} lag={lag} launches={mat.get_info("launches_per_mult"):.0f} passes={mat.get_info("passes"):.0f} '
                   f'{ms:.3f} ms  model {model/ms/1e6:.0f} GB/s  compulsory {mat.get_info("compulsory_bytes")/ms/1e6:.0f} GB/s',
                   flush=True)
         mat.destroy()
