@@ -64,7 +64,9 @@ struct Globals {
   int device = -1;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // side stream: remote (NVLink) passes overlap the local ones
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double *d_scratch = nullptr;  // SCRATCH_DOUBLES
   double *h_scratch = nullptr;  // pinned, SCRATCH_DOUBLES
   double *d_partials = nullptr; // per-block partial sums

@@ -139,6 +139,14 @@ extern "C" int dnm_init(int device)
   G.device = device;
   G.sm_count = prop.multiProcessorCount;
   DNM_CHECK_CUDA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  {
+    // the side stream outranks the main one so its few persistent CTAs get SM slots first
+    int lo = 0, hi = 0;
+    DNM_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    DNM_CHECK_CUDA(cudaStreamCreateWithPriority(&G.stream2, cudaStreamNonBlocking, hi));
+  }
+  DNM_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_fork, cudaEventDisableTiming));
+  DNM_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_join, cudaEventDisableTiming));
   DNM_CHECK_CUDA(cudaEventCreate(&G.ev_start));
   DNM_CHECK_CUDA(cudaEventCreate(&G.ev_stop));
   DNM_CHECK_CUDA(cudaMalloc(&G.d_scratch, sizeof(double) * SCRATCH_DOUBLES));
@@ -163,6 +171,9 @@ extern "C" int dnm_finalize(void)
   cudaFreeHost(G.h_scratch);
   cudaEventDestroy(G.ev_start);
   cudaEventDestroy(G.ev_stop);
+  cudaEventDestroy(G.ev_fork);
+  cudaEventDestroy(G.ev_join);
+  cudaStreamDestroy(G.stream2);
   cudaStreamDestroy(G.stream);
   G = Globals();
   DNM_API_END

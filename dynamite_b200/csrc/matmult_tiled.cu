@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <map>
+#include <string>
 #include <memory>
 
 #include "tiled_kernel.cuh"
@@ -32,6 +33,10 @@ namespace dnm {
 namespace {
 
 using namespace tiled;
+
+// stream the launch helpers below enqueue on (the side stream while remote passes are issued)
+cudaStream_t g_launch_stream = nullptr;
+inline cudaStream_t launch_stream() { return g_launch_stream ? g_launch_stream : G.stream; }
 
 // Plain gather for masks no window can hold, and for index spaces smaller
 // than one tile.  Terms in global index coordinates (sw/rb unused).
@@ -201,6 +206,11 @@ struct TiledPlan {
   std::vector<Direct> directs;
   Direct all;  // every mask, for the row-local helpers (diag, norm)
   bool any_remote = false;
+  bool overlap = false;      // (peer-load mode) remote passes accumulate into y_remote on the side stream
+  cplx *y_remote = nullptr;  // [local rows], allocated on first use
+  bool dma = false;          // remote shards are staged by the copy engines while the local passes run
+  cplx *stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev_staged[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   double cost = 0.0;  // estimated HBM sweeps per MatMult
   ~TiledPlan()
   {
@@ -211,6 +221,12 @@ struct TiledPlan {
     for (void *q : all.owned) cudaFree(q);
     for (auto &u : units)
       if (u.d_sync) cudaFree(u.d_sync);
+    if (y_remote) cudaFree(y_remote);
+    for (int b = 0; b < 2; ++b) {
+      if (stage[b]) cudaFree(stage[b]);
+      if (ev_staged[b]) cudaEventDestroy(ev_staged[b]);
+      if (ev_free[b]) cudaEventDestroy(ev_free[b]);
+    }
   }
 };
 
@@ -518,7 +534,7 @@ struct PlanInputs {
 };
 
 template <int T, int R, bool SMALL>
-void launch_tiled_v(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
+void launch_tiled_v(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles, const cplx *y_extra)
 {
   static bool attr_set = false;
   const size_t smem = sizeof(double2) << T;
@@ -527,16 +543,16 @@ void launch_tiled_v(const Pass &ps, const cplx *x, cplx *y, const double *diag, 
     DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled<T, R, SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
-  k_tiled<T, R, SMALL><<<(unsigned)ntiles, TileCfg<T, R>::NT, smem, G.stream>>>(ps.p, ps.st, x, y, diag);
+  k_tiled<T, R, SMALL><<<(unsigned)ntiles, TileCfg<T, R>::NT, smem, launch_stream()>>>(ps.p, ps.st, x, y, diag, y_extra);
   count_launch();
   DNM_CHECK_CUDA(cudaGetLastError());
 }
 
 template <int T, int R>
-void launch_tiled(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
+void launch_tiled(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles, const cplx *y_extra)
 {
-  if (ps.small) launch_tiled_v<T, R, true>(ps, x, y, diag, ntiles);
-  else launch_tiled_v<T, R, false>(ps, x, y, diag, ntiles);
+  if (ps.small) launch_tiled_v<T, R, true>(ps, x, y, diag, ntiles, y_extra);
+  else launch_tiled_v<T, R, false>(ps, x, y, diag, ntiles, y_extra);
 }
 
 // rows per thread for a tile size: 16 by default (8 on request) where the CTA stays >= 64 threads
@@ -547,10 +563,10 @@ int rows_for(int T, int want)
   return (want == 16) ? 16 : 8;  // 8 rows/thread (64 registers) doubles the resident warps; measured faster
 }
 
-void launch_pass(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
+void launch_pass(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles, const cplx *y_extra = nullptr)
 {
 #define DNM_TILE_CASE(TT, RR) \
-  if (ps.T == TT && ps.R == RR) return launch_tiled<TT, RR>(ps, x, y, diag, ntiles);
+  if (ps.T == TT && ps.R == RR) return launch_tiled<TT, RR>(ps, x, y, diag, ntiles, y_extra);
   DNM_TILE_CASE(8, 4)
   DNM_TILE_CASE(9, 8)
   DNM_TILE_CASE(10, 8)
@@ -573,7 +589,7 @@ int direct_grid(i64 rows)
 }
 
 template <int T, int R>
-void launch_fused_tr(const Unit &u, const cplx *x, cplx *y, const double *diag)
+void launch_fused_tr(const Unit &u, const cplx *x, cplx *y, const double *diag, int ctas_per_sm)
 {
   static int occ = 0;
   const size_t smem = sizeof(double2) << T;
@@ -583,18 +599,18 @@ void launch_fused_tr(const Unit &u, const cplx *x, cplx *y, const double *diag)
     DNM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tiled_fused<T, R>, TileCfg<T, R>::NT, smem));
     if (occ < 1) occ = 1;
   }
-  DNM_CHECK_CUDA(cudaMemsetAsync(u.d_sync, 0, u.sync_bytes, G.stream));
-  const unsigned long long cap = (unsigned long long)G.sm_count * occ;
+  DNM_CHECK_CUDA(cudaMemsetAsync(u.d_sync, 0, u.sync_bytes, launch_stream()));
+  const unsigned long long cap = (unsigned long long)G.sm_count * (ctas_per_sm > 0 ? std::min(ctas_per_sm, occ) : occ);
   const unsigned grid = (unsigned)std::min<unsigned long long>(cap, u.fp.nitems);
-  k_tiled_fused<T, R><<<grid, TileCfg<T, R>::NT, smem, G.stream>>>(u.fp, x, y, diag);
+  k_tiled_fused<T, R><<<grid, TileCfg<T, R>::NT, smem, launch_stream()>>>(u.fp, x, y, diag);
   count_launch();
   DNM_CHECK_CUDA(cudaGetLastError());
 }
 
-void launch_fused(const Unit &u, int T, int R, const cplx *x, cplx *y, const double *diag)
+void launch_fused(const Unit &u, int T, int R, const cplx *x, cplx *y, const double *diag, int ctas_per_sm = 0)
 {
 #define DNM_FUSE_CASE(TT, RR) \
-  if (T == TT && R == RR) return launch_fused_tr<TT, RR>(u, x, y, diag);
+  if (T == TT && R == RR) return launch_fused_tr<TT, RR>(u, x, y, diag, ctas_per_sm);
   DNM_FUSE_CASE(8, 4)
   DNM_FUSE_CASE(9, 8)
   DNM_FUSE_CASE(10, 8)
@@ -640,7 +656,9 @@ void build_units(TiledPlan &plan, int verbose)
     }
     // local small passes always run in the persistent kernel (it prefetches through the L2),
     // fused when more than one pass shares a chunk
-    if (u.passes.size() > 1 || (fuse_bits > 0 && first.small && first.peer_xor == 0 && getenv("DNM_PERSISTENT"))) {
+    const bool remote_persistent = plan.overlap && first.small && first.peer_xor != 0;
+    if (u.passes.size() > 1 || remote_persistent ||
+        (fuse_bits > 0 && first.small && first.peer_xor == 0 && getenv("DNM_PERSISTENT"))) {
       const int ubits = popc64(U);
       u.fused = true;
       FusedParams &fp = u.fp;
@@ -650,6 +668,7 @@ void build_units(TiledPlan &plan, int verbose)
       fp.nchunks = (long long)1 << (nloc - ubits);
       fp.nitems = (unsigned long long)(fp.nchunks + (long long)(fp.npasses - 1) * lag) * fp.npasses << fp.log_tiles;
       fp.diag_pass = -1;
+      fp.prefetch = first.peer_xor == 0 ? 1 : 0;
       for (int k = 0; k < fp.npasses; ++k) {
         const Pass &ps = plan.passes[u.passes[k]];
         fp.p[k] = ps.p;
@@ -715,11 +734,26 @@ std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &mas
       plan->any_remote = true;
     }
   } else {
-    bool first = true;
+    // With remote groups, their passes run on a side stream into a separate buffer while the
+    // local passes run (NVLink-bound and HBM-bound work overlap); the first remote pass then
+    // WRITES that buffer, exactly like the first local pass writes y.
+    // Remote groups: default = DMA staging (copy engines pull the partner shard over NVLink into a
+    // local buffer while the SMs run the local passes; the group's passes then run on local memory).
+    // DNM_REMOTE=peer keeps the in-kernel NVLink loads, DNM_REMOTE=peer_overlap runs them on a side stream.
+    const char *rmode = getenv("DNM_REMOTE");
+    const std::string mode = rmode ? rmode : "dma";
+    plan->dma = groups.size() > 1 && mode == "dma";
+    plan->overlap = groups.size() > 1 && mode == "peer_overlap";
+    bool first_local = true, first_remote = true;
     for (auto &kv : groups) {
-      plan_group(*plan, kv.second, kv.first, T, R, B, first, verbose);
-      first = false;
-      if (kv.first != 0) plan->any_remote = true;
+      if (kv.first == 0) {
+        plan_group(*plan, kv.second, kv.first, T, R, B, first_local, verbose);
+        first_local = false;
+      } else {
+        plan_group(*plan, kv.second, kv.first, T, R, B, plan->overlap && first_remote, verbose);
+        first_remote = false;
+        plan->any_remote = true;
+      }
     }
   }
   // cost in vector sweeps over HBM: a writing pass reads x and writes y (2), an
@@ -813,26 +847,150 @@ void tiled_mult(dnm_mat_s *A, dnm_vec_t xv, dnm_vec_t yv)
 
   if (plan.any_remote) stream_barrier();  // every rank's x is complete before anyone pulls from it
 
-  bool first = true;
-  for (const Unit &u : plan.units) {
+  if (plan.dma && plan.any_remote) {
+    const size_t bytes = sizeof(cplx) * (size_t)nloc_rows;
+    // distinct partners in pass order
+    std::vector<int> partners;
+    for (const Pass &ps : plan.passes)
+      if (ps.peer_xor && std::find(partners.begin(), partners.end(), ps.peer_xor) == partners.end())
+        partners.push_back(ps.peer_xor);
+    for (const Direct &d : plan.directs)
+      if (d.peer_xor && std::find(partners.begin(), partners.end(), d.peer_xor) == partners.end())
+        partners.push_back(d.peer_xor);
+    const int nbuf = partners.size() > 1 ? 2 : 1;
+    for (int b = 0; b < nbuf; ++b) {
+      if (!plan.stage[b]) DNM_CHECK_CUDA(cudaMalloc(&plan.stage[b], bytes));
+      if (!plan.ev_staged[b]) DNM_CHECK_CUDA(cudaEventCreateWithFlags(&plan.ev_staged[b], cudaEventDisableTiming));
+      if (!plan.ev_free[b]) DNM_CHECK_CUDA(cudaEventCreateWithFlags(&plan.ev_free[b], cudaEventDisableTiming));
+    }
+    DNM_CHECK_CUDA(cudaEventRecord(G.ev_fork, G.stream));
+    DNM_CHECK_CUDA(cudaStreamWaitEvent(G.stream2, G.ev_fork, 0));
+    // local passes on the SMs ...
+    bool first = true;
+    for (const Unit &u : plan.units) {
+      const Pass &ps = plan.passes[u.passes.front()];
+      if (ps.peer_xor != 0) continue;
+      const double *diag = (first && plan.use_diag) ? A->d_diag : nullptr;
+      if (u.fused) launch_fused(u, ps.T, ps.R, xv->d, y, plan.use_diag ? A->d_diag : nullptr);
+      else launch_pass(ps, xv->d, y, diag, nloc_rows >> ps.T);
+      first = false;
+      ++launches;
+    }
+    for (const Direct &d : plan.directs) {
+      if (d.peer_xor != 0) continue;
+      const double *diag = (first && plan.use_diag) ? A->d_diag : nullptr;
+      k_xor_direct<<<direct_grid(nloc_rows), 256, 0, G.stream>>>(d.p, xv->d, y, diag, nloc_rows);
+      count_launch();
+      DNM_CHECK_CUDA(cudaGetLastError());
+      first = false;
+      ++launches;
+    }
+    // ... while the copy engines stage the partner shards, two buffers deep
+    for (size_t gi = 0; gi < partners.size(); ++gi) {
+      const int b = (int)(gi % nbuf);
+      if ((int)gi >= nbuf) DNM_CHECK_CUDA(cudaStreamWaitEvent(G.stream2, plan.ev_free[b], 0));
+      DNM_CHECK_CUDA(cudaMemcpyAsync(plan.stage[b], source(partners[gi]), bytes, cudaMemcpyDeviceToDevice, G.stream2));
+      DNM_CHECK_CUDA(cudaEventRecord(plan.ev_staged[b], G.stream2));
+      // the group's passes read the staged copy as ordinary local memory
+      DNM_CHECK_CUDA(cudaStreamWaitEvent(G.stream, plan.ev_staged[b], 0));
+      for (const Unit &u : plan.units) {
+        const Pass &ps = plan.passes[u.passes.front()];
+        if (ps.peer_xor != partners[gi]) continue;
+        if (u.fused) launch_fused(u, ps.T, ps.R, plan.stage[b], y, nullptr);
+        else launch_pass(ps, plan.stage[b], y, nullptr, nloc_rows >> ps.T);
+        ++launches;
+      }
+      for (const Direct &d : plan.directs) {
+        if (d.peer_xor != partners[gi]) continue;
+        k_xor_direct<<<direct_grid(nloc_rows), 256, 0, G.stream>>>(d.p, plan.stage[b], y, nullptr, nloc_rows);
+        count_launch();
+        DNM_CHECK_CUDA(cudaGetLastError());
+        ++launches;
+      }
+      DNM_CHECK_CUDA(cudaEventRecord(plan.ev_free[b], G.stream));
+    }
+    stream_barrier();  // every peer has finished copying out of x
+    A->launches_per_mult = launches;
+    return;
+  }
+
+  const bool overlap = plan.overlap && plan.any_remote;
+  cplx *yr = nullptr;
+  if (overlap) {
+    if (!plan.y_remote) DNM_CHECK_CUDA(cudaMalloc(&plan.y_remote, sizeof(cplx) * (size_t)nloc_rows));
+    yr = plan.y_remote;
+    // fork: the side stream starts once x is globally ready
+    DNM_CHECK_CUDA(cudaEventRecord(G.ev_fork, G.stream));
+    DNM_CHECK_CUDA(cudaStreamWaitEvent(G.stream2, G.ev_fork, 0));
+    int remote_ctas = 1;
+    if (const char *e = getenv("DNM_REMOTE_CTAS")) remote_ctas = std::max(1, atoi(e));
+    g_launch_stream = G.stream2;
+    try {
+      for (const Unit &u : plan.units) {
+        const Pass &ps = plan.passes[u.passes.front()];
+        if (ps.peer_xor == 0) continue;
+        // a few resident CTAs per SM keep the NVLink busy and leave the rest of the SM to the local passes
+        if (u.fused) launch_fused(u, ps.T, ps.R, source(ps.peer_xor), yr, nullptr, remote_ctas);
+        else launch_pass(ps, source(ps.peer_xor), yr, nullptr, nloc_rows >> ps.T);
+        ++launches;
+      }
+      for (const Direct &d : plan.directs) {
+        if (d.peer_xor == 0) continue;
+        k_xor_direct<<<direct_grid(nloc_rows), 256, 0, G.stream2>>>(d.p, source(d.peer_xor), yr, nullptr, nloc_rows);
+        count_launch();
+        DNM_CHECK_CUDA(cudaGetLastError());
+        ++launches;
+      }
+    } catch (...) {
+      g_launch_stream = nullptr;
+      throw;
+    }
+    g_launch_stream = nullptr;
+    DNM_CHECK_CUDA(cudaEventRecord(G.ev_join, G.stream2));
+  }
+
+  // local work (and, without overlap, the remote passes too) on the main stream
+  int last_local = -1;
+  bool local_directs = false;
+  for (size_t k = 0; k < plan.units.size(); ++k)
+    if (plan.passes[plan.units[k].passes.front()].peer_xor == 0) last_local = (int)k;
+  for (const Direct &d : plan.directs) local_directs = local_directs || d.peer_xor == 0;
+
+  bool first = true, joined = !overlap;
+  for (size_t k = 0; k < plan.units.size(); ++k) {
+    const Unit &u = plan.units[k];
     const Pass &ps = plan.passes[u.passes.front()];
+    if (overlap && ps.peer_xor != 0) continue;
     const cplx *x = source(ps.peer_xor);
     const double *diag = (first && plan.use_diag) ? A->d_diag : nullptr;
     if (u.fused) {
       launch_fused(u, ps.T, ps.R, x, y, plan.use_diag ? A->d_diag : nullptr);
     } else {
-      launch_pass(ps, x, y, diag, nloc_rows >> ps.T);
+      const cplx *extra = nullptr;
+      if (overlap && (int)k == last_local && !local_directs && ps.p.accumulate) {
+        // the last local pass also folds in the remote contributions: join the side stream first
+        DNM_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_join, 0));
+        extra = yr;
+        joined = true;
+      }
+      launch_pass(ps, x, y, diag, nloc_rows >> ps.T, extra);
     }
     first = false;
     ++launches;
   }
   for (const Direct &d : plan.directs) {
+    if (overlap && d.peer_xor != 0) continue;
     const cplx *x = source(d.peer_xor);
     const double *diag = (first && plan.use_diag) ? A->d_diag : nullptr;
     k_xor_direct<<<direct_grid(nloc_rows), 256, 0, G.stream>>>(d.p, x, y, diag, nloc_rows);
     count_launch();
     DNM_CHECK_CUDA(cudaGetLastError());
     first = false;
+    ++launches;
+  }
+  if (!joined) {
+    DNM_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_join, 0));
+    vec_axpby(y, yr, nloc_rows, make_double2(1.0, 0.0), make_double2(1.0, 0.0));
     ++launches;
   }
 

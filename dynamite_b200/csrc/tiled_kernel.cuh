@@ -164,7 +164,8 @@ __device__ __forceinline__ void prefetch_tile_l2(const PassParams &P, const cplx
 template <int T, int R, bool SMALL>
 __device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables &S, i64 outer, i64 base_g,
                                           const cplx *__restrict__ x, cplx *__restrict__ y,
-                                          const double *__restrict__ diag, double2 *tile, double *csign)
+                                          const double *__restrict__ diag, double2 *tile, double *csign,
+                                          const cplx *__restrict__ y_extra = nullptr)
 {
   constexpr int NT = TileCfg<T, R>::NT;
   constexpr int LOG_NT = TileCfg<T, R>::LOG_NT;
@@ -263,6 +264,18 @@ __device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables
 #pragma unroll
     for (int r = 0; r < R; ++r) cp_async16(&tile[tid + r * NT], &y[base_g | P.roff[r]]);
     cp_async_wait_all();
+    if (y_extra != nullptr) {
+      // a second addend (the remote contributions gathered on the side stream)
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const double2 old = tile[tid + r * NT];
+        ar[r] += old.x;
+        ai[r] += old.y;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) cp_async16(&tile[tid + r * NT], &y_extra[base_g | P.roff[r]]);
+      cp_async_wait_all();
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const double2 old = tile[tid + r * NT];  // written by this thread's own copies
@@ -278,12 +291,13 @@ __device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables
 template <int T, int R, bool SMALL>
 __global__ void __launch_bounds__(TileCfg<T, R>::NT, TileCfg<T, R>::MINB)
     k_tiled(const __grid_constant__ PassParams P, const __grid_constant__ SmallTables S,
-            const cplx *__restrict__ x, cplx *__restrict__ y, const double *__restrict__ diag)
+            const cplx *__restrict__ x, cplx *__restrict__ y, const double *__restrict__ diag,
+            const cplx *__restrict__ y_extra)
 {
   extern __shared__ double2 tile[];
   __shared__ double csign[SMALL ? SMALL_TERMS : 1];
   const i64 outer = tile_outer_bits(P, blockIdx.x);
-  tile_body<T, R, SMALL>(P, S, outer, thread_base(P, outer), x, y, diag, tile, csign);
+  tile_body<T, R, SMALL>(P, S, outer, thread_base(P, outer), x, y, diag, tile, csign, y_extra);
 }
 
 // ---- L2-fused passes ---------------------------------------------------------------------
@@ -309,6 +323,7 @@ struct FusedParams {
   int *done;               // [(npasses-1) * nchunks] tiles finished per (pass, chunk)
   unsigned long long *ticket;
   int diag_pass;           // pass that applies the cached diagonal (-1: none)
+  int prefetch;            // warm the L2 with the next tile (local x only: peer memory bypasses the L2)
 };
 
 template <int T, int R>
@@ -348,7 +363,7 @@ __global__ void __launch_bounds__(TileCfg<T, R>::NT, TileCfg<T, R>::MINB)
       const i64 outer = tile_outer_bits(P, tile_id);
       const i64 base_g = thread_base(P, outer);
       // the old y of this tile is needed only at the end: start pulling it into the L2 now
-      if (P.accumulate) prefetch_tile_l2<R>(P, y, base_g);
+      if (P.accumulate && F.prefetch) prefetch_tile_l2<R>(P, y, base_g);
       if (k > 0) {
         if (threadIdx.x == 0) {
           const volatile int *flag = F.done + (size_t)(k - 1) * F.nchunks + c;
@@ -362,7 +377,7 @@ __global__ void __launch_bounds__(TileCfg<T, R>::NT, TileCfg<T, R>::MINB)
         int kn;
         long long cn;
         unsigned long long tn;
-        if (decode(s_item, kn, cn, tn)) {
+        if (F.prefetch && decode(s_item, kn, cn, tn)) {
           const PassParams &Pn = F.p[kn];
           prefetch_tile_l2<R>(Pn, x, thread_base(Pn, tile_outer_bits(Pn, tn)));
         }
