@@ -79,6 +79,11 @@ struct Globals {
 extern Globals G;
 
 void require_init();
+// Krylov workspace vectors are recycled between solves (small problems are allocation-bound otherwise)
+dnm_vec_t pool_acquire(int64_t global_n);
+void pool_release(dnm_vec_t v);
+void pool_clear();
+int64_t pool_count(int64_t global_n);
 inline void count_launch(int n = 1) { G.launches += n; }
 
 // ---- objects behind the opaque handles --------------------------------------

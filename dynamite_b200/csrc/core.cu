@@ -29,6 +29,53 @@ void require_init()
               "dynamite_b200: no CUDA device bound (call dnm_init; this backend has no CPU fallback)");
 }
 
+// ---- workspace pool -------------------------------------------------------------
+static std::vector<dnm_vec_t> g_pool;
+
+int64_t pool_count(int64_t global_n)
+{
+  int64_t c = 0;
+  for (dnm_vec_t v : g_pool) c += v->global_n == global_n;
+  return c;
+}
+
+void pool_clear()
+{
+  std::vector<dnm_vec_t> old;
+  old.swap(g_pool);
+  for (dnm_vec_t v : old) dnm_vec_destroy(v);
+}
+
+dnm_vec_t pool_acquire(int64_t global_n)
+{
+  for (size_t i = 0; i < g_pool.size(); ++i)
+    if (g_pool[i]->global_n == global_n) {
+      dnm_vec_t v = g_pool[i];
+      g_pool.erase(g_pool.begin() + i);
+      return v;
+    }
+  if (!g_pool.empty()) pool_clear();  // a different problem size: give the memory back first
+  dnm_vec_t v = nullptr;
+  const int rc = dnm_vec_create(global_n, &v);
+  if (rc) throw Fail{rc};
+  return v;
+}
+
+void pool_release(dnm_vec_t v)
+{
+  if (!v) return;
+  // keep at most a quarter of the device memory parked in the pool
+  size_t f = 0, t = 0;
+  cudaMemGetInfo(&f, &t);
+  size_t pooled = 0;
+  for (dnm_vec_t q : g_pool) pooled += sizeof(cplx) * (size_t)q->local_n;
+  if (pooled + sizeof(cplx) * (size_t)v->local_n > t / 4 || g_pool.size() >= 256) {
+    dnm_vec_destroy(v);
+    return;
+  }
+  g_pool.push_back(v);
+}
+
 // ---- HostSubspace -----------------------------------------------------------
 
 void HostSubspace::copy_from(const dnm_subspace_t *s)
@@ -162,6 +209,7 @@ extern "C" int dnm_finalize(void)
   DNM_API_BEGIN
   if (!G.inited) return DNM_OK;
   cudaStreamSynchronize(G.stream);
+  pool_clear();
   if (G.nccl_comm) {
     ncclCommDestroy((ncclComm_t)G.nccl_comm);
     G.nccl_comm = nullptr;
@@ -481,7 +529,12 @@ extern "C" int dnm_vec_create(int64_t n, dnm_vec_t *out)
   v->local_n = n / G.nranks;
   v->local_start = v->local_n * G.rank;
   try {
-    DNM_CHECK_CUDA(cudaMalloc(&v->d, sizeof(cplx) * v->local_n));
+    if (cudaMalloc(&v->d, sizeof(cplx) * v->local_n) != cudaSuccess) {
+      cudaGetLastError();
+      v->d = nullptr;
+      if (G.nranks == 1) pool_clear();  // parked workspace may be what is in the way
+      DNM_CHECK_CUDA(cudaMalloc(&v->d, sizeof(cplx) * v->local_n));
+    }
     DNM_CHECK_CUDA(cudaMemsetAsync(v->d, 0, sizeof(cplx) * v->local_n, G.stream));
     if (G.nranks > 1) share_with_peers(v);
   } catch (...) {

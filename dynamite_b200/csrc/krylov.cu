@@ -114,7 +114,7 @@ struct Basis {
   int64_t nloc = 0;
   ~Basis()
   {
-    for (dnm_vec_t q : owned) dnm_vec_destroy(q);
+    for (dnm_vec_t q : owned) pool_release(q);
   }
   cplx *ptr(int j) const { return v[j]->d; }
 };
@@ -178,12 +178,13 @@ void arnoldi_column(dnm_mat_t A, Basis &B, int j, double *d_H, int ld, double *d
   vec_scale_dev(w, B.nloc, S.norm, true);
 }
 
-int64_t vector_budget(int64_t local_n)
+int64_t vector_budget(int64_t local_n, int64_t global_n)
 {
   size_t f = 0, t = 0;
   DNM_CHECK_CUDA(cudaMemGetInfo(&f, &t));
   const int64_t reserve = (int64_t)512 << 20;
-  return std::max<int64_t>(0, ((int64_t)f - reserve) / (int64_t)(sizeof(cplx) * local_n));
+  // workspace already parked in the pool counts as available
+  return std::max<int64_t>(0, ((int64_t)f - reserve) / (int64_t)(sizeof(cplx) * local_n)) + pool_count(global_n);
 }
 
 // wall-clock phase accounting, printed when DNM_TRACE is set
@@ -239,7 +240,7 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
   int m = ncv > 0 ? ncv : (int)std::min<int64_t>(30, N);  // SLEPc MFN default
   m = (int)std::min<int64_t>(m, N);
   // basis: y doubles as v[0]; m+1 more vectors (v[1..m] and the A*v[m] probe)
-  const int64_t fit = vector_budget(nloc);
+  const int64_t fit = vector_budget(nloc, N);
   if (m + 1 > fit) {
     DNM_REQUIRE(fit >= 3, DNM_ERR_MEM, "not enough device memory for a Krylov basis (room for %lld vectors)",
                 (long long)fit);
@@ -263,9 +264,7 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
   B.nloc = nloc;
   B.v.push_back(y);
   for (int j = 0; j < m + 1; ++j) {
-    dnm_vec_t q = nullptr;
-    int rc = dnm_vec_create(N, &q);
-    if (rc) return rc;
+    dnm_vec_t q = pool_acquire(N);
     B.owned.push_back(q);
     B.v.push_back(q);
   }
@@ -439,7 +438,7 @@ extern "C" int dnm_eigsolve(dnm_mat_t A, int nev, int which, double tol, int max
   // SLEPc defaults: ncv = max(2*nev, nev+15), capped by the dimension
   if (ncv <= 0) ncv = std::max(2 * nev, nev + 15);
   ncv = (int)std::min<int64_t>(ncv, N);
-  const int64_t fit = vector_budget(nloc);
+  const int64_t fit = vector_budget(nloc, N);
   if (ncv + 1 > fit) {
     DNM_REQUIRE(fit >= nev + 3, DNM_ERR_MEM, "not enough device memory for the Lanczos basis (room for %lld vectors)",
                 (long long)fit);
@@ -451,9 +450,7 @@ extern "C" int dnm_eigsolve(dnm_mat_t A, int nev, int which, double tol, int max
   Basis B;
   B.nloc = nloc;
   for (int j = 0; j < ncv + 1; ++j) {
-    dnm_vec_t q = nullptr;
-    int rc = dnm_vec_create(N, &q);
-    if (rc) return rc;
+    dnm_vec_t q = pool_acquire(N);
     B.owned.push_back(q);
     B.v.push_back(q);
   }
@@ -499,7 +496,9 @@ extern "C" int dnm_eigsolve(dnm_mat_t A, int nev, int which, double tol, int max
   std::vector<double> spike(ncv, 0.0);  // coupling of kept Ritz vectors to the first new Lanczos vector
   std::vector<double> resid(ncv, 0.0);
   int nconv = 0, l = 0, its = 0, matmults = 0, reason = 0;
+  PhaseTimer trace;
   random_unit(0, 0);
+  trace.mark(0);
 
   while (reason == 0) {
     ++its;
@@ -511,7 +510,9 @@ extern "C" int dnm_eigsolve(dnm_mat_t A, int nev, int which, double tol, int max
       ++matmults;
     }
     DNM_CHECK_CUDA(cudaMemcpyAsync(h_H.data(), d_H, hbytes, cudaMemcpyDeviceToHost, G.stream));
+    trace.mark(1);
     DNM_CHECK_CUDA(cudaStreamSynchronize(G.stream));
+    trace.mark(2);
     auto Hre = [&](int i, int j) { return h_H[2 * ((size_t)ld * j + i)]; };
     bool breakdown = false;
     for (int j = k0; j < nv; ++j)
@@ -570,6 +571,7 @@ extern "C" int dnm_eigsolve(dnm_mat_t A, int nev, int which, double tol, int max
     }
     const int nkeep = done ? k : k + lnew;
 
+    trace.mark(3);
     // rotate the basis: V[:, nconv : nconv+nkeep] = V[:, nconv:nv] * Z[:, order[0:nkeep]]
     if (nkeep > 0) {
       std::vector<double> Q((size_t)na * nkeep);
@@ -583,6 +585,7 @@ extern "C" int dnm_eigsolve(dnm_mat_t A, int nev, int which, double tol, int max
       DNM_CHECK_CUDA(cudaGetLastError());
       DNM_CHECK_CUDA(cudaStreamSynchronize(G.stream));  // Q is a host temporary
     }
+    trace.mark(4);
     for (int i = 0; i < nkeep; ++i) {
       theta[nconv + i] = w[order[i]];
       spike[nconv + i] = (i < k) ? 0.0 : beta * Z[(size_t)order[i] * na + (na - 1)];
@@ -616,6 +619,8 @@ extern "C" int dnm_eigsolve(dnm_mat_t A, int nev, int which, double tol, int max
     }
   }
   DNM_CHECK_CUDA(cudaStreamSynchronize(G.stream));
+  trace.mark(6);
+  trace.report("eigsolve (combine = basis rotation)");
   *nconv_out = nret;
   if (reason_out) *reason_out = reason;
   if (its_out) *its_out = its;

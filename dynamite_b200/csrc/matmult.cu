@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstring>
 #include <memory>
+#include <type_traits>
 
 #include "context.h"
 #include "matmult_tiled.h"
@@ -66,6 +67,92 @@ __global__ void __launch_bounds__(TPB)
       double cr, ci;
       mask_element(msc, mi, bra, cr, ci);
       const cplx xv = x[col];
+      ar += cr * xv.x - ci * xv.y;
+      ai += cr * xv.y + ci * xv.x;
+    }
+    y[row] = make_double2(ar, ai);
+  }
+}
+
+// SpinConserve -> the same SpinConserve sector (the BASELINE eigsolve config): the row index IS
+// the rank of the ket, so the column is row + rank_delta over the few bits the mask spans, and
+// the binomial table is staged in shared memory.  Bit-exact with S2I (tests/test_gpu_matmult.py).
+// NARROW: chains of at most 31 spins run the integer work in 32-bit registers (states, ranks and
+// binomials all fit), which halves the instruction count of this issue-bound kernel.
+template <bool NARROW>
+__global__ void __launch_bounds__(TPB)
+    k_mult_spinconserve(SubSpinConserve sub, MscDev msc, const double *__restrict__ diag, const cplx *__restrict__ x,
+                        cplx *__restrict__ y, i64 M)
+{
+  typedef typename std::conditional<NARROW, unsigned int, unsigned long long>::type state_t;
+  typedef typename std::conditional<NARROW, int, i64>::type rank_t;
+  extern __shared__ unsigned char s_raw[];
+  rank_t *tab = reinterpret_cast<rank_t *>(s_raw);
+  const int ld = (int)sub.ld, k = (int)sub.k, L = (int)sub.L;
+  for (int i = threadIdx.x; i < (k + 1) * ld; i += blockDim.x) tab[i] = (rank_t)sub.nck[i];
+  __syncthreads();
+
+  auto popc = [](state_t v) -> int { return NARROW ? __popc((unsigned int)v) : __popcll((unsigned long long)v); };
+  auto ctz = [](state_t v) -> int { return NARROW ? __ffs((int)v) - 1 : __ffsll((long long)v) - 1; };
+  auto clz = [](state_t v) -> int { return NARROW ? __clz((int)v) : __clzll((long long)v); };
+  constexpr int TOP = NARROW ? 31 : 63;
+
+  for (i64 row = blockIdx.x * (i64)blockDim.x + threadIdx.x; row < M; row += (i64)gridDim.x * blockDim.x) {
+    // unrank (bsubspace_impl.h:210-228)
+    state_t ket = 0;
+    {
+      rank_t idx = (rank_t)row;
+      int kk = k;
+      for (int n = L; n > 0; --n) {
+        ket <<= 1;
+        const rank_t c = (kk > n - 1) ? 0 : tab[kk * ld + n - 1];
+        if (idx >= c) {
+          idx -= c;
+          --kk;
+          ket |= 1;
+        }
+      }
+    }
+    double ar = 0.0, ai = 0.0;
+    int mi = 0;
+    if (diag != nullptr) {
+      const cplx xv = x[row];
+      const double d = diag[row];
+      ar = d * xv.x;
+      ai = d * xv.y;
+      mi = 1;
+    }
+    for (; mi < msc.nmasks; ++mi) {
+      const state_t mask = (state_t)__ldg(&msc.masks[mi]);
+      const state_t bra = ket ^ mask;
+      if (popc(bra) != k) continue;  // leaves the sector
+      rank_t delta = 0;
+      if (mask != 0) {
+        // only the set bits inside the span of the mask change their (position, ordinal) pair
+        const int lo = ctz(mask), hi = TOP - clz(mask);
+        const state_t below_mask = ((state_t)1 << lo) - 1;
+        const state_t span = (hi == TOP ? ~(state_t)0 : (((state_t)1 << (hi + 1)) - 1)) & ~below_mask;
+        const int below = popc(ket & below_mask);
+        state_t b = bra & span;
+        int j = below;
+        while (b) {
+          const int n = ctz(b);
+          ++j;
+          if (j <= n) delta += tab[j * ld + n];
+          b &= b - 1;
+        }
+        state_t a = ket & span;
+        j = below;
+        while (a) {
+          const int n = ctz(a);
+          ++j;
+          if (j <= n) delta -= tab[j * ld + n];
+          a &= a - 1;
+        }
+      }
+      double cr, ci;
+      mask_element(msc, mi, (i64)bra, cr, ci);
+      const cplx xv = x[row + (i64)delta];
       ar += cr * xv.x - ci * xv.y;
       ai += cr * xv.y + ci * xv.x;
     }
@@ -227,6 +314,19 @@ void validate_msc(int64_t nmasks, const int64_t *masks, const int64_t *offs, con
 void general_mult(dnm_mat_s *A, const cplx *x, cplx *y)
 {
   const i64 M = A->M;
+  const dnm_subspace_t &l = A->left.desc, &r = A->right.desc;
+  if (l.type == DNM_SPIN_CONSERVE && r.type == DNM_SPIN_CONSERVE && l.L == r.L && l.k == r.k && l.L < 63 &&
+      getenv("DNM_NO_SC_KERNEL") == nullptr) {
+    const SubSpinConserve sub = A->right.spin_dev();
+    const size_t smem = sizeof(i64) * (size_t)((sub.k + 1) * sub.ld);
+    if (smem <= 48 * 1024) {
+      if (l.L <= 31) k_mult_spinconserve<true><<<row_grid(M), TPB, smem, G.stream>>>(sub, A->msc, A->d_diag, x, y, M);
+      else k_mult_spinconserve<false><<<row_grid(M), TPB, smem, G.stream>>>(sub, A->msc, A->d_diag, x, y, M);
+      count_launch();
+      DNM_CHECK_CUDA(cudaGetLastError());
+      return;
+    }
+  }
   with_sub(A->left, [&](auto ls) {
     with_sub(A->right, [&](auto rs) {
       k_mult_general<<<row_grid(M), TPB, 0, G.stream>>>(ls, rs, A->msc, A->d_diag, x, y, M);

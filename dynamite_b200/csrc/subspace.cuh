@@ -39,6 +39,16 @@ DNM_HD int ctz64(i64 v)
 #endif
 }
 
+// leading zero bits; v != 0
+DNM_HD int clz64(i64 v)
+{
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)v);
+#else
+  return __builtin_clzll((unsigned long long)v);
+#endif
+}
+
 struct SubFull {
   i64 L;
   DNM_HD i64 dim() const { return (i64)1 << L; }
@@ -79,6 +89,33 @@ struct SubSpinConserve {
   {
     if (popc64(state) != (int)k) return -1;
     return rank_nocheck(state);
+  }
+  // rank(bra) - rank(ket) for bra = ket ^ mask with equal popcounts (mask != 0): only the set
+  // bits inside the span of the mask change their (position, ordinal) pair, so the sum runs
+  // over those few bits instead of all k.  Exact integer arithmetic: same result as s2i(bra).
+  DNM_HD i64 rank_delta(i64 ket, i64 bra, i64 mask) const
+  {
+    const int lo = ctz64(mask);
+    const int hi = 63 - clz64(mask);
+    const i64 span = (hi == 63 ? (i64)-1 : (((i64)1 << (hi + 1)) - 1)) & ~(((i64)1 << lo) - 1);
+    const i64 below = popc64(ket & (((i64)1 << lo) - 1));
+    i64 delta = 0;
+    i64 b = bra & span, j = below;
+    while (b) {
+      const int n = ctz64(b);
+      ++j;
+      if (j <= n) delta += nck[j * ld + n];
+      b &= b - 1;
+    }
+    i64 a = ket & span;
+    j = below;
+    while (a) {
+      const int n = ctz64(a);
+      ++j;
+      if (j <= n) delta -= nck[j * ld + n];
+      a &= a - 1;
+    }
+    return delta;
   }
   DNM_HD i64 i2s(i64 idx) const
   {

@@ -50,28 +50,26 @@ __device__ __forceinline__ void block_reduce_store(const double (&acc)[NV], doub
   }
 }
 
-// d_out[c] = reduce_b partials[b*nv + c]
+// d_out[c] = reduce_b partials[b*nv + c]; one block per component c
 __global__ void k_final_reduce(const double *__restrict__ partials, int nblocks, int nv, double *__restrict__ d_out,
                                int is_max, const int *__restrict__ active)
 {
   if (active != nullptr && *active == 0) return;
   __shared__ double sh[TPB / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int c = 0; c < nv; ++c) {
-    double v = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
-      const double p = partials[(size_t)b * nv + c];
-      v = is_max ? fmax(v, p) : v + p;
-    }
-    v = is_max ? warp_max(v) : warp_sum(v);
-    if (lane == 0) sh[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-      double t = (lane < TPB / 32) ? sh[lane] : 0.0;
-      t = is_max ? warp_max(t) : warp_sum(t);
-      if (lane == 0) d_out[c] = t;
-    }
-    __syncthreads();
+  const int c = blockIdx.x;
+  double v = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+    const double p = partials[(size_t)b * nv + c];
+    v = is_max ? fmax(v, p) : v + p;
+  }
+  v = is_max ? warp_max(v) : warp_sum(v);
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double t = (lane < TPB / 32) ? sh[lane] : 0.0;
+    t = is_max ? warp_max(t) : warp_sum(t);
+    if (lane == 0) d_out[c] = t;
   }
 }
 
@@ -248,7 +246,7 @@ double *partials_for(int nblocks, int nv)
 
 void finish(int nblocks, int nv, double *d_out, bool is_max, const int *d_active = nullptr)
 {
-  k_final_reduce<<<1, TPB, 0, G.stream>>>(G.d_partials, nblocks, nv, d_out, is_max ? 1 : 0, d_active);
+  k_final_reduce<<<nv, TPB, 0, G.stream>>>(G.d_partials, nblocks, nv, d_out, is_max ? 1 : 0, d_active);
   count_launch();
   DNM_CHECK_CUDA(cudaGetLastError());
   if (is_max) allreduce_max_dev(d_out, nv);

@@ -183,3 +183,27 @@ def test_error_paths(gpu):
     with pytest.raises(BackendError, match='in place'):
         mat.mult(x, x)
     mat.destroy()
+
+
+def test_spinconserve_rank_delta_random_masks(gpu):
+    """Same-sector SpinConserve uses row + rank_delta instead of a full re-rank: stress it with
+    number-conserving hops over arbitrary distances (2- and 4-site flips) and long sign strings."""
+    R = np.random.RandomState(23)
+    for L, k in ((16, 8), (18, 5), (20, 3), (33, 2)):
+        terms = {}
+        for _ in range(40):
+            nflip = R.choice([2, 4])
+            sites = R.choice(L, size=nflip, replace=False)
+            mask = int(sum(1 << int(s) for s in sites))
+            sign = int(R.randint(0, 1 << min(L, 30))) & ~mask      # sign string away from the flipped sites
+            terms[(mask, sign)] = float(R.uniform(-1, 1))           # popcount(mask & sign) = 0 -> real coefficient
+        terms[(0, 0b1011)] = 0.37
+        tlist = sorted((m, s, c) for (m, s), c in terms.items())
+        spec = {'type': 'spinconserve', 'L': L, 'k': k}
+        sub = oracle.Subspace(spec)
+        x = rand_state(sub.dim, 77)
+        want = oracle.matmult(oracle.Msc.from_terms(tlist), sub, sub, x)
+        for diag in (False, True):
+            mat = product_mat(tlist, spec, spec, precompute_diag=diag)
+            assert rel_err(device_mult(mat, x), want) < TOL, (L, k, diag)
+            mat.destroy()
