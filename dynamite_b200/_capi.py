@@ -15,7 +15,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdynamite_b200.so')
+# DNM_LIB overrides the library path (A/B timing of builds); normally the in-tree build is used
+LIB_PATH = os.environ.get('DNM_LIB') or os.path.join(_HERE, 'libdynamite_b200.so')
 
 i64p = C.POINTER(C.c_int64)
 f64p = C.POINTER(C.c_double)

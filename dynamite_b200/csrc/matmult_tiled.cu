@@ -534,7 +534,7 @@ struct PlanInputs {
 };
 
 template <int T, int R, bool SMALL>
-void launch_tiled_v(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles, const cplx *y_extra)
+void launch_tiled_v(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
 {
   static bool attr_set = false;
   const size_t smem = sizeof(double2) << T;
@@ -543,16 +543,16 @@ void launch_tiled_v(const Pass &ps, const cplx *x, cplx *y, const double *diag, 
     DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled<T, R, SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
-  k_tiled<T, R, SMALL><<<(unsigned)ntiles, TileCfg<T, R>::NT, smem, launch_stream()>>>(ps.p, ps.st, x, y, diag, y_extra);
+  k_tiled<T, R, SMALL><<<(unsigned)ntiles, TileCfg<T, R>::NT, smem, launch_stream()>>>(ps.p, ps.st, x, y, diag);
   count_launch();
   DNM_CHECK_CUDA(cudaGetLastError());
 }
 
 template <int T, int R>
-void launch_tiled(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles, const cplx *y_extra)
+void launch_tiled(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
 {
-  if (ps.small) launch_tiled_v<T, R, true>(ps, x, y, diag, ntiles, y_extra);
-  else launch_tiled_v<T, R, false>(ps, x, y, diag, ntiles, y_extra);
+  if (ps.small) launch_tiled_v<T, R, true>(ps, x, y, diag, ntiles);
+  else launch_tiled_v<T, R, false>(ps, x, y, diag, ntiles);
 }
 
 // rows per thread for a tile size: 16 by default (8 on request) where the CTA stays >= 64 threads
@@ -563,10 +563,10 @@ int rows_for(int T, int want)
   return (want == 16) ? 16 : 8;  // 8 rows/thread (64 registers) doubles the resident warps; measured faster
 }
 
-void launch_pass(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles, const cplx *y_extra = nullptr)
+void launch_pass(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
 {
 #define DNM_TILE_CASE(TT, RR) \
-  if (ps.T == TT && ps.R == RR) return launch_tiled<TT, RR>(ps, x, y, diag, ntiles, y_extra);
+  if (ps.T == TT && ps.R == RR) return launch_tiled<TT, RR>(ps, x, y, diag, ntiles);
   DNM_TILE_CASE(8, 4)
   DNM_TILE_CASE(9, 8)
   DNM_TILE_CASE(10, 8)
@@ -950,12 +950,6 @@ void tiled_mult(dnm_mat_s *A, dnm_vec_t xv, dnm_vec_t yv)
   }
 
   // local work (and, without overlap, the remote passes too) on the main stream
-  int last_local = -1;
-  bool local_directs = false;
-  for (size_t k = 0; k < plan.units.size(); ++k)
-    if (plan.passes[plan.units[k].passes.front()].peer_xor == 0) last_local = (int)k;
-  for (const Direct &d : plan.directs) local_directs = local_directs || d.peer_xor == 0;
-
   bool first = true, joined = !overlap;
   for (size_t k = 0; k < plan.units.size(); ++k) {
     const Unit &u = plan.units[k];
@@ -966,14 +960,7 @@ void tiled_mult(dnm_mat_s *A, dnm_vec_t xv, dnm_vec_t yv)
     if (u.fused) {
       launch_fused(u, ps.T, ps.R, x, y, plan.use_diag ? A->d_diag : nullptr);
     } else {
-      const cplx *extra = nullptr;
-      if (overlap && (int)k == last_local && !local_directs && ps.p.accumulate) {
-        // the last local pass also folds in the remote contributions: join the side stream first
-        DNM_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_join, 0));
-        extra = yr;
-        joined = true;
-      }
-      launch_pass(ps, x, y, diag, nloc_rows >> ps.T, extra);
+      launch_pass(ps, x, y, diag, nloc_rows >> ps.T);
     }
     first = false;
     ++launches;

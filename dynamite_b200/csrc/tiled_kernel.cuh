@@ -164,8 +164,7 @@ __device__ __forceinline__ void prefetch_tile_l2(const PassParams &P, const cplx
 template <int T, int R, bool SMALL>
 __device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables &S, i64 outer, i64 base_g,
                                           const cplx *__restrict__ x, cplx *__restrict__ y,
-                                          const double *__restrict__ diag, double2 *tile, double *csign,
-                                          const cplx *__restrict__ y_extra = nullptr)
+                                          const double *__restrict__ diag, double2 *tile, double *csign)
 {
   constexpr int NT = TileCfg<T, R>::NT;
   constexpr int LOG_NT = TileCfg<T, R>::LOG_NT;
@@ -264,18 +263,6 @@ __device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables
 #pragma unroll
     for (int r = 0; r < R; ++r) cp_async16(&tile[tid + r * NT], &y[base_g | P.roff[r]]);
     cp_async_wait_all();
-    if (y_extra != nullptr) {
-      // a second addend (the remote contributions gathered on the side stream)
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const double2 old = tile[tid + r * NT];
-        ar[r] += old.x;
-        ai[r] += old.y;
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r) cp_async16(&tile[tid + r * NT], &y_extra[base_g | P.roff[r]]);
-      cp_async_wait_all();
-    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const double2 old = tile[tid + r * NT];  // written by this thread's own copies
@@ -291,13 +278,12 @@ __device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables
 template <int T, int R, bool SMALL>
 __global__ void __launch_bounds__(TileCfg<T, R>::NT, TileCfg<T, R>::MINB)
     k_tiled(const __grid_constant__ PassParams P, const __grid_constant__ SmallTables S,
-            const cplx *__restrict__ x, cplx *__restrict__ y, const double *__restrict__ diag,
-            const cplx *__restrict__ y_extra)
+            const cplx *__restrict__ x, cplx *__restrict__ y, const double *__restrict__ diag)
 {
   extern __shared__ double2 tile[];
   __shared__ double csign[SMALL ? SMALL_TERMS : 1];
   const i64 outer = tile_outer_bits(P, blockIdx.x);
-  tile_body<T, R, SMALL>(P, S, outer, thread_base(P, outer), x, y, diag, tile, csign, y_extra);
+  tile_body<T, R, SMALL>(P, S, outer, thread_base(P, outer), x, y, diag, tile, csign);
 }
 
 // ---- L2-fused passes ---------------------------------------------------------------------
