@@ -168,6 +168,46 @@ class State:
         self.assert_initialized()
         return self.vec.getArray()
 
+    # ---- checkpoint / resume ---------------------------------------------------------
+    _VEC_CLASSID = 1211214   # PETSc VEC_FILE_CLASSID
+
+    def save(self, fname):
+        """``<fname>.vec`` in PETSc's binary Vec layout (big-endian int64 class id and length --
+        the 64-bit-index build the reference needs for L > 31 -- then interleaved complex128) and
+        ``<fname>.metadata`` = the pickled subspace, as reference ``states.py:627-652``.
+        Single-rank for now: rank r would write its block at offset 16 + 16*local_start."""
+        import pickle
+        self.assert_initialized()
+        if COMM_WORLD.size != 1:
+            raise NotImplementedError('State.save is single-rank in this backend')
+        with open(fname + '.metadata', 'wb') as f:
+            pickle.dump(self.subspace, f)
+        n = len(self)
+        with open(fname + '.vec', 'wb') as f:
+            f.write(np.array([self._VEC_CLASSID, n], dtype='>i8').tobytes())
+            block = 1 << 22
+            for a in range(0, n, block):
+                b = min(n, a + block)
+                f.write(self.vec[a:b].astype('>c16').tobytes())
+
+    @classmethod
+    def from_file(cls, fname):
+        """inverse of :meth:`save` (uses ``pickle``: do not load untrusted files)"""
+        import pickle
+        with open(fname + '.metadata', 'rb') as f:
+            subspace = pickle.load(f)
+        with open(fname + '.vec', 'rb') as f:
+            classid, n = np.frombuffer(f.read(16), dtype='>i8')
+            if classid != cls._VEC_CLASSID or subspace.get_dimension() != n:
+                raise RuntimeError('corrupt data encountered when loading state from file')
+            rtn = cls(subspace=subspace)
+            block = 1 << 22
+            for a in range(0, n, block):
+                b = min(n, a + block)
+                rtn.vec[a:b] = np.frombuffer(f.read(16 * (b - a)), dtype='>c16').astype(np.complex128)
+        rtn.set_initialized()
+        return rtn
+
     # ---- algebra --------------------------------------------------------------------
     def dot(self, x):
         """<self|x> (conjugate-linear in self)"""

@@ -242,3 +242,44 @@ def test_rdm_subspaces_vs_oracle(gpu, spec):
         want = oracle.rdm(psi, osub, keep)
         assert np.allclose(got, want, atol=1e-13), keep
         assert abs(np.trace(got) - 1) < 1e-12
+
+
+def test_state_api_and_checkpoint(gpu, tmp_path):
+    """State surface used around the path: products, projection, XParity conversion, save/load."""
+    from dynamite_b200.hamiltonians import build_hamiltonian
+    from dynamite_b200.states import State, UninitializedError
+    from dynamite_b200.subspaces import Full, SpinConserve, XParity
+    s = State(L=6, state='UDUDUD')
+    assert s.to_numpy()[0b101010] == 1 and abs(s.norm() - 1) < 1e-15
+    with pytest.raises(UninitializedError):
+        State(L=6).assert_initialized()
+    with pytest.raises(ValueError):
+        State(subspace=SpinConserve(6, 3), state='UUUUUU')
+    r = State(L=8, state='random', seed=4)
+    R = np.random.RandomState(4)
+    want = R.standard_normal(256) + 1j * R.standard_normal(256)     # reference stream, states.py:272-318
+    assert np.allclose(r.to_numpy(), want / np.linalg.norm(want), atol=1e-15)
+    # save / from_file round trip
+    r.save(str(tmp_path / 'ckpt'))
+    back = State.from_file(str(tmp_path / 'ckpt'))
+    assert np.array_equal(back.to_numpy(), r.to_numpy()) and back.subspace == r.subspace
+    # projection
+    p = r.copy()
+    p.project(3, 1)
+    v = p.to_numpy()
+    idx = np.arange(256)
+    assert np.all(v[((idx >> 3) & 1) == 0] == 0) and abs(p.norm() - 1) < 1e-14
+    # XParity <-> parent conversion is an isometry onto the sector, and H commutes with it
+    parent = SpinConserve(8, 4)
+    xp = XParity(parent, sector='-')
+    sx = State(subspace=xp, state='random', seed=9)
+    up = xp.convert_state(sx)
+    assert up.subspace is parent and abs(up.norm() - 1) < 1e-13
+    down = xp.convert_state(up)
+    assert np.allclose(down.to_numpy(), sx.to_numpy(), atol=1e-14)
+    H = build_hamiltonian('heisenberg', 8)
+    H.add_subspace(xp)
+    H.add_subspace(parent)
+    lhs = xp.convert_state(H.dot(sx))          # convert(H_x psi)
+    rhs = H.dot(up)                            # H_parent convert(psi)
+    assert np.allclose(lhs.to_numpy(), rhs.to_numpy(), atol=1e-13)
