@@ -208,6 +208,8 @@ struct TiledPlan {
   bool any_remote = false;
   bool overlap = false;      // (peer-load mode) remote passes accumulate into y_remote on the side stream
   cplx *y_remote = nullptr;  // [local rows], allocated on first use
+  PassParams *d_batch = nullptr;  // all passes' parameters, when the whole product runs as one batched launch
+  int batch_T = 0, batch_R = 0;
   bool dma = false;          // remote shards are staged by the copy engines while the local passes run
   cplx *stage[2] = {nullptr, nullptr};
   cudaEvent_t ev_staged[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
@@ -222,6 +224,7 @@ struct TiledPlan {
     for (auto &u : units)
       if (u.d_sync) cudaFree(u.d_sync);
     if (y_remote) cudaFree(y_remote);
+    if (d_batch) cudaFree(d_batch);
     for (int b = 0; b < 2; ++b) {
       if (stage[b]) cudaFree(stage[b]);
       if (ev_staged[b]) cudaEventDestroy(ev_staged[b]);
@@ -433,6 +436,9 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
   ps.nmasks = (int)masks.size();
   ps.nterms = (int)sw.size();
   ps.wbits = wbits;
+  // large passes stage csign/sw/rb (16 B per term) in shared memory when that still leaves two tiles per SM
+  ps.p.staged = (!(ps.p.ngroups <= SMALL_GROUPS && ps.nterms <= SMALL_TERMS) && (size_t)ps.nterms * 16 <= 40 * 1024 &&
+                 getenv("DNM_NO_STAGE") == nullptr) ? 1 : 0;
   ps.small = ps.p.ngroups <= SMALL_GROUPS && ps.nterms <= SMALL_TERMS;
   if (ps.small) {
     for (int g = 0; g < ps.p.ngroups; ++g) {
@@ -537,9 +543,10 @@ template <int T, int R, bool SMALL>
 void launch_tiled_v(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
 {
   static bool attr_set = false;
-  const size_t smem = sizeof(double2) << T;
+  const size_t smem = (sizeof(double2) << T) + (ps.p.staged ? (size_t)ps.nterms * 16 : 0);
   if (!attr_set) {
-    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled<T, R, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled<T, R, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)((sizeof(double2) << T) + 40 * 1024)));
     DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled<T, R, SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
@@ -623,6 +630,40 @@ void launch_fused(const Unit &u, int T, int R, const cplx *x, cplx *y, const dou
   DNM_FUSE_CASE(13, 16)
 #undef DNM_FUSE_CASE
   DNM_REQUIRE(false, DNM_ERR_INTERNAL, "no fused kernel for T=%d R=%d", T, R);
+}
+
+template <int T, int R>
+void launch_batch_tr(const TiledPlan &plan, const cplx *x, cplx *y, const double *diag)
+{
+  static bool attr_set = false;
+  const size_t smem = sizeof(double2) << T;
+  if (!attr_set) {
+    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_batch<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_batch<T, R>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_set = true;
+  }
+  const dim3 grid((unsigned)((long long)1 << (plan.nloc - T)), (unsigned)plan.passes.size());
+  k_tiled_batch<T, R><<<grid, TileCfg<T, R>::NT, smem, G.stream>>>(plan.d_batch, x, y, diag, plan.use_diag ? 0 : -1);
+  count_launch();
+  DNM_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_batch(const TiledPlan &plan, const cplx *x, cplx *y, const double *diag)
+{
+#define DNM_BATCH_CASE(TT, RR) \
+  if (plan.batch_T == TT && plan.batch_R == RR) return launch_batch_tr<TT, RR>(plan, x, y, diag);
+  DNM_BATCH_CASE(8, 4)
+  DNM_BATCH_CASE(9, 8)
+  DNM_BATCH_CASE(10, 8)
+  DNM_BATCH_CASE(10, 16)
+  DNM_BATCH_CASE(11, 8)
+  DNM_BATCH_CASE(11, 16)
+  DNM_BATCH_CASE(12, 8)
+  DNM_BATCH_CASE(12, 16)
+  DNM_BATCH_CASE(13, 8)
+  DNM_BATCH_CASE(13, 16)
+#undef DNM_BATCH_CASE
+  DNM_REQUIRE(false, DNM_ERR_INTERNAL, "no batched kernel for T=%d R=%d", plan.batch_T, plan.batch_R);
 }
 
 // Group consecutive local passes whose windows together span few enough bits for their
@@ -802,6 +843,28 @@ TiledPlan *build_plan(dnm_mat_s *A)
               cand->passes.size(), cand->directs.size(), cand->cost);
     if (!best || cand->cost < best->cost - 1e-9) best = std::move(cand);
   }
+  // Small problems (a pass has fewer tiles than the GPU has CTA slots) with several passes: run all
+  // passes concurrently as one grid and combine in y with FP64 atomics.
+  if (best && G.nranks == 1 && best->directs.empty() && best->passes.size() >= 3 && getenv("DNM_NO_BATCH") == nullptr) {
+    const Pass &p0 = best->passes[0];
+    const long long ntiles = (long long)1 << (best->nloc - p0.T);
+    bool same = true;
+    for (const Pass &ps : best->passes) same = same && ps.T == p0.T && ps.R == p0.R && ps.peer_xor == 0;
+    if (same && ntiles <= 4LL * G.sm_count && best->passes.size() < 65536) {
+      std::vector<PassParams> all;
+      for (const Pass &ps : best->passes) {
+        PassParams q = ps.p;
+        q.accumulate = 2;
+        q.staged = 0;
+        all.push_back(q);
+      }
+      DNM_CHECK_CUDA(cudaMalloc(&best->d_batch, sizeof(PassParams) * all.size()));
+      DNM_CHECK_CUDA(cudaMemcpyAsync(best->d_batch, all.data(), sizeof(PassParams) * all.size(), cudaMemcpyHostToDevice,
+                                     G.stream));
+      best->batch_T = p0.T;
+      best->batch_R = p0.R;
+    }
+  }
   DNM_CHECK_CUDA(cudaStreamSynchronize(G.stream));
   return best.release();
 }
@@ -844,6 +907,13 @@ void tiled_mult(dnm_mat_s *A, dnm_vec_t xv, dnm_vec_t yv)
     DNM_REQUIRE(ptr != nullptr, DNM_ERR_COMM, "input vector is not mapped on peer rank %d", G.rank ^ peer_xor);
     return ptr;
   };
+
+  if (plan.d_batch) {
+    DNM_CHECK_CUDA(cudaMemsetAsync(y, 0, sizeof(cplx) * (size_t)nloc_rows, G.stream));
+    launch_batch(plan, xv->d, y, plan.use_diag ? A->d_diag : nullptr);
+    A->launches_per_mult = 1;
+    return;
+  }
 
   if (plan.any_remote) stream_barrier();  // every rank's x is complete before anyone pulls from it
 

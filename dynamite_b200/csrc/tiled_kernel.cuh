@@ -35,7 +35,8 @@ struct PassParams {
   int nterms;
   int B;           // log2 of the contiguous run length
   int n_outer;     // number of index bits outside the window
-  int accumulate;  // 0: y = ..., 1: y += ...
+  int accumulate;  // 0: y = ..., 1: y += ... (read-modify-write), 2: y += ... with FP64 atomics (batched passes)
+  int staged;      // large pass whose per-term tables are staged in shared memory behind the tile
   // group tables [ngroups]
   const u32 *lam;  // mask in window coordinates
   const u16 *t0;   // first term (terms t0..t1 have no r bits in their sign mask)
@@ -174,10 +175,18 @@ __device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables
   // stage the tile: runs of 2^B contiguous amplitudes, asynchronous 16-byte copies
 #pragma unroll
   for (int r = 0; r < R; ++r) cp_async16(&tile[tid + r * NT], &x[base_g | P.roff[r]]);
+  uint2 *swrb = reinterpret_cast<uint2 *>(csign + P.nterms);  // staged passes only
   if (SMALL) {
     // coefficient with the tile-uniform sign applied, once per tile
     for (int t = tid; t < P.nterms; t += NT)
       csign[t] = flip_sign(S.cf[t], __popcll((unsigned long long)(S.so[t] & outer_g)) & 1);
+  } else if (P.staged) {
+    // many-term passes (SYK): the same, plus the window sign bits, staged once per tile so the
+    // per-thread term loop reads shared memory instead of four global tables
+    for (int t = tid; t < P.nterms; t += NT) {
+      csign[t] = flip_sign(__ldg(&P.cf[t]), __popcll((unsigned long long)(__ldg(&P.so[t]) & outer_g)) & 1);
+      swrb[t] = make_uint2(__ldg(&P.sw[t]), __ldg(&P.rb[t]));
+    }
   }
   cp_async_wait_all();
   __syncthreads();
@@ -199,6 +208,7 @@ __device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables
   // coefficient of term t with tile and thread signs applied
   auto term = [&](int t) -> double {
     if (SMALL) return flip_sign(csign[t], __popc(S.sw[t] & (u32)tid) & 1);
+    if (P.staged) return flip_sign(csign[t], __popc(swrb[t].x & (u32)tid) & 1);
     const int p = (__popcll((unsigned long long)(__ldg(&P.so[t]) & outer_g)) ^ __popc(__ldg(&P.sw[t]) & (u32)tid)) & 1;
     return flip_sign(__ldg(&P.cf[t]), p);
   };
@@ -241,7 +251,7 @@ __device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables
         for (int r = 0; r < R; ++r) d[r] = c0;
         for (int t = t1; t < t2; ++t) {
           const double c = term(t);
-          const u32 bits = SMALL ? S.rb[t] : __ldg(&P.rb[t]);
+          const u32 bits = SMALL ? S.rb[t] : (P.staged ? swrb[t].y : __ldg(&P.rb[t]));
           const int chi = __double2hiint(c), clo = __double2loint(c);
 #pragma unroll
           for (int r = 0; r < R; ++r) d[r] += flip_if(chi, clo, bits, r);
@@ -257,7 +267,15 @@ __device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables
     }
   }
 
-  if (P.accumulate) {
+  if (P.accumulate == 2) {
+    // passes of a small problem run concurrently in one grid: combine in the L2 with FP64 atomics
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double *dst = reinterpret_cast<double *>(y + (base_g | P.roff[r]));
+      atomicAdd(dst, ar[r]);
+      atomicAdd(dst + 1, ai[r]);
+    }
+  } else if (P.accumulate) {
     // reuse the tile buffer to fetch the previous pass's y with full memory-level parallelism
     __syncthreads();
 #pragma unroll
@@ -281,9 +299,28 @@ __global__ void __launch_bounds__(TileCfg<T, R>::NT, TileCfg<T, R>::MINB)
             const cplx *__restrict__ x, cplx *__restrict__ y, const double *__restrict__ diag)
 {
   extern __shared__ double2 tile[];
-  __shared__ double csign[SMALL ? SMALL_TERMS : 1];
+  __shared__ double csign_small[SMALL ? SMALL_TERMS : 1];
+  // staged large passes keep their term tables in dynamic shared memory right behind the tile
+  double *csign = SMALL ? csign_small : reinterpret_cast<double *>(tile + (1 << T));
   const i64 outer = tile_outer_bits(P, blockIdx.x);
   tile_body<T, R, SMALL>(P, S, outer, thread_base(P, outer), x, y, diag, tile, csign);
+}
+
+// every pass of a small problem in ONE launch (blockIdx.y = pass): a pass of an L2-resident vector
+// has too few tiles to fill the GPU, and the passes only interact through y, which is combined
+// with atomics.  Tables come from global memory (PassParams array on the device).
+template <int T, int R>
+__global__ void __launch_bounds__(TileCfg<T, R>::NT, TileCfg<T, R>::MINB)
+    k_tiled_batch(const PassParams *__restrict__ Ps, const cplx *__restrict__ x, cplx *__restrict__ y,
+                  const double *__restrict__ diag, int diag_pass)
+{
+  extern __shared__ double2 tile[];
+  const PassParams &P = Ps[blockIdx.y];
+  const SmallTables &unused = *reinterpret_cast<const SmallTables *>(Ps);  // never read when SMALL == false
+  double *csign = reinterpret_cast<double *>(tile + (1 << T));
+  const i64 outer = tile_outer_bits(P, blockIdx.x);
+  tile_body<T, R, false>(P, unused, outer, thread_base(P, outer), x, y, ((int)blockIdx.y == diag_pass) ? diag : nullptr,
+                         tile, csign);
 }
 
 // ---- L2-fused passes ---------------------------------------------------------------------
