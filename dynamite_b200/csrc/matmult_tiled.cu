@@ -362,11 +362,24 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
 
   // groups: (mask, real|imaginary); inside a group the terms whose sign mask has no
   // row bits come first
-  std::vector<u32> lam, sw, rb;
+  std::vector<u32> lam, sw, rb, toff;
   std::vector<u16> t0, t1, t2, pat;
   std::vector<u8> kp;
   std::vector<i64> so;
-  std::vector<double> cf;
+  std::vector<double> cf, tabs;
+  std::vector<unsigned long long> rpat;
+  // coefficient tables (PATH_TABLE) are only worth it, and only supported, in passes that are too
+  // big for the constant-memory variant anyway
+  size_t general_terms = 0, general_groups = 0;
+  for (const NMask *nm : masks) {
+    bool re = false, im = false;
+    for (const NTerm &t : nm->terms) (t.imag ? im : re) = true;
+    general_groups += (re ? 1 : 0) + (im ? 1 : 0);
+    general_terms += nm->terms.size();
+  }
+  const bool allow_tables = R <= 8 && !(general_groups <= (size_t)SMALL_GROUPS && general_terms <= (size_t)SMALL_TERMS) &&
+                            getenv("DNM_NO_TABLES") == nullptr;
+  bool any_table = false;
   for (const NMask *nm : masks) {
     const u32 l = extract(nm->mask & lmask);
     for (int kind = 0; kind < 2; ++kind) {
@@ -377,7 +390,73 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
       }
       if (plain.empty() && rowdep.empty()) continue;
       lam.push_back(l);
+      toff.push_back(0);
+      rpat.push_back(0);
       t0.push_back((u16)sw.size());
+      if (allow_tables && plain.size() + rowdep.size() >= 4) {
+        // GF(2) basis of the sign masks; coords[t] = which basis vectors XOR to term t's mask
+        std::vector<const NTerm *> all(plain);
+        all.insert(all.end(), rowdep.begin(), rowdep.end());
+        std::vector<i64> basis, reduced;       // original-form basis vectors and their eliminated forms
+        std::vector<u32> red_coord;            // coordinates (in `basis`) of each eliminated form
+        std::vector<u32> coords(all.size(), 0);
+        bool ok = true;
+        for (size_t ti = 0; ti < all.size() && ok; ++ti) {
+          i64 v = all[ti]->sign;
+          u32 c = 0;
+          for (bool changed = true; changed;) {  // reduced[] is not kept in echelon order: iterate to a fixed point
+            changed = false;
+            for (size_t k = 0; k < reduced.size(); ++k) {
+              const i64 top = (i64)1 << (63 - __builtin_clzll((unsigned long long)reduced[k]));
+              if (v & top) {
+                v ^= reduced[k];
+                c ^= red_coord[k];
+                changed = true;
+              }
+            }
+          }
+          if (v != 0) {
+            if (basis.size() >= 6) {
+              ok = false;
+              break;
+            }
+            // new independent vector: the term's own mask joins the basis
+            const u32 self = 1u << basis.size();
+            basis.push_back(all[ti]->sign);
+            reduced.push_back(v);
+            red_coord.push_back(c ^ self);
+            c = self;
+          }
+          coords[ti] = c;
+        }
+        if (ok) {
+          const int d = (int)basis.size();
+          toff.back() = (u32)tabs.size();
+          for (u32 p = 0; p < (1u << d); ++p) {
+            double acc = 0.0;
+            for (size_t ti = 0; ti < all.size(); ++ti) acc += (__builtin_parity(coords[ti] & p) ? -1.0 : 1.0) * all[ti]->coef;
+            tabs.push_back(acc);
+          }
+          unsigned long long rp = 0;
+          for (int k = 0; k < d; ++k) {
+            const u32 w = extract(basis[k] & lmask);
+            const u32 bits = row_pattern(w);
+            sw.push_back(w);
+            rb.push_back(bits);
+            so.push_back(basis[k] & ~wbits);
+            cf.push_back(0.0);
+            for (int r = 0; r < R; ++r)
+              if ((bits >> r) & 1u) rp |= (unsigned long long)1 << (8 * r + k);
+          }
+          rpat.back() = rp;
+          t1.push_back((u16)sw.size());
+          t2.push_back((u16)sw.size());
+          pat.push_back(0);
+          kp.push_back((u8)(kind | (PATH_TABLE << 1)));
+          any_table = true;
+          continue;
+        }
+      }
       for (const NTerm *t : plain) {
         sw.push_back(extract(t->sign & lmask));
         rb.push_back(0);
@@ -425,6 +504,9 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
   ps.p.t2 = up(t2, ps.owned);
   ps.p.pat = up(pat, ps.owned);
   ps.p.kp = up(kp, ps.owned);
+  ps.p.tabs = up(tabs, ps.owned);
+  ps.p.toff = up(toff, ps.owned);
+  ps.p.rpat = up(rpat, ps.owned);
   ps.p.sw = up(sw, ps.owned);
   ps.p.rb = up(rb, ps.owned);
   ps.p.so = up(so, ps.owned);
@@ -437,9 +519,9 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
   ps.nterms = (int)sw.size();
   ps.wbits = wbits;
   // large passes stage csign/sw/rb (16 B per term) in shared memory when that still leaves two tiles per SM
-  ps.p.staged = (!(ps.p.ngroups <= SMALL_GROUPS && ps.nterms <= SMALL_TERMS) && (size_t)ps.nterms * 16 <= 40 * 1024 &&
+  ps.p.staged = ((any_table || !(ps.p.ngroups <= SMALL_GROUPS && ps.nterms <= SMALL_TERMS)) && (size_t)ps.nterms * 16 <= 40 * 1024 &&
                  getenv("DNM_NO_STAGE") == nullptr) ? 1 : 0;
-  ps.small = ps.p.ngroups <= SMALL_GROUPS && ps.nterms <= SMALL_TERMS;
+  ps.small = !any_table && ps.p.ngroups <= SMALL_GROUPS && ps.nterms <= SMALL_TERMS;
   if (ps.small) {
     for (int g = 0; g < ps.p.ngroups; ++g) {
       ps.st.lam[g] = lam[g];

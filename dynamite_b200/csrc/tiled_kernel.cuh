@@ -28,7 +28,7 @@ typedef unsigned char u8;
 constexpr int SMALL_GROUPS = 48;  // passes up to this size keep their tables in kernel-parameter
 constexpr int SMALL_TERMS = 96;   // (constant) memory; bigger ones read them from global memory
 
-enum { PATH_SCALAR = 0, PATH_TWO = 1, PATH_GENERAL = 2 };
+enum { PATH_SCALAR = 0, PATH_TWO = 1, PATH_GENERAL = 2, PATH_TABLE = 3 };
 
 struct PassParams {
   int ngroups;
@@ -44,6 +44,12 @@ struct PassParams {
   const u16 *t2;   // one past the last term
   const u16 *pat;  // PATH_TWO: bit r = sign of the r-dependent terms on row group r
   const u8 *kp;    // bit 0: imaginary coefficients, bits 1..2: path
+  // PATH_TABLE groups (many terms per mask): the terms' sign masks span a GF(2) space of dimension
+  // d <= 6; the group's "terms" t0..t1 are the d basis vectors and the coefficient of a row is
+  // tabs[toff + index], index bit k = parity(basis_k & row)
+  const double *tabs;
+  const u32 *toff;                 // [ngroups]
+  const unsigned long long *rpat;  // [ngroups] byte r = index bits contributed by row group r
   // term tables [nterms]
   const u32 *sw;   // sign bits inside the window (window coordinates)
   const u32 *rb;   // bit r = parity((sw >> LOG_NT) & r)
@@ -226,7 +232,8 @@ __device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables
     const int path = kp >> 1;
 
     double c0 = 0.0;  // terms without r bits: one scalar per thread
-    for (int t = t0; t < t1; ++t) c0 += term(t);
+    if (SMALL || path != PATH_TABLE)
+      for (int t = t0; t < t1; ++t) c0 += term(t);
 
     const double2 *col = tile + base;
     if (path == PATH_SCALAR) {
@@ -246,6 +253,23 @@ __device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables
 #pragma unroll
         for (int r = 0; r < R; ++r) d[r] = ((pat >> r) & 1u) ? dm : dp;
         any = (dp != 0.0) || (dm != 0.0);
+      } else if (!SMALL && path == PATH_TABLE) {
+        // index of this thread's rows into the group's coefficient table: one parity per basis vector
+        u32 q = 0;
+        for (int t = t0; t < t1; ++t) {
+          u32 p;
+          if (P.staged) p = (u32)(__double2hiint(csign[t]) >> 31) ^ (u32)__popc(swrb[t].x & (u32)tid);
+          else p = (u32)__popcll((unsigned long long)(__ldg(&P.so[t]) & outer_g)) ^ (u32)__popc(__ldg(&P.sw[t]) & (u32)tid);
+          q |= (p & 1u) << (t - t0);
+        }
+        const unsigned long long rp = __ldg(&P.rpat[g]);
+        const double *tab = P.tabs + __ldg(&P.toff[g]);
+        any = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          d[r] = __ldg(&tab[q ^ (u32)((rp >> (8 * (r & 7))) & 0xffull)]);
+          any = any || (d[r] != 0.0);
+        }
       } else {
 #pragma unroll
         for (int r = 0; r < R; ++r) d[r] = c0;
