@@ -17,8 +17,8 @@
 namespace dnm {
 namespace {
 
-constexpr int TILE = 32;
-constexpr int KC = 32;
+constexpr int TILE = 64;  // output tile edge; 16x16 threads, 4x4 complex accumulators each
+constexpr int KC = 16;    // traced states staged per step
 
 struct RdmParams {
   int L, k;
@@ -27,6 +27,7 @@ struct RdmParams {
   i64 dim;        // 2^k
   i64 tr_begin, tr_end;
   i64 tr_per_slice;
+  int ntiles;     // tiles per edge; blockIdx.x enumerates the upper triangle (a_tile <= b_tile)
   int nloc_bits;  // >= 0: vector is sharded, owner = idx >> nloc_bits
   const cplx *peer[MAX_RANKS];
 };
@@ -53,56 +54,96 @@ __device__ __forceinline__ cplx amplitude(const S &sub, const RdmParams &P, i64 
   return P.peer[idx >> P.nloc_bits][idx & (((i64)1 << P.nloc_bits) - 1)];
 }
 
+// rho is Hermitian: only tiles on or above the diagonal are computed (the host mirrors them).
 template <class S>
 __global__ void __launch_bounds__(256) k_rdm(S sub, RdmParams P, double *__restrict__ rho)
 {
   __shared__ double2 As[KC][TILE + 1];
   __shared__ double2 Bs[KC][TILE + 1];
+  __shared__ i64 dep_a[TILE], dep_b[TILE], dep_t[KC];
+  // upper-triangle tile pair from the linear block index
+  int ta = 0, rem = blockIdx.x;
+  while (rem >= P.ntiles - ta) {
+    rem -= P.ntiles - ta;
+    ++ta;
+  }
+  const int tb = ta + rem;
+  const bool diag_tile = (ta == tb);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const i64 a0 = (i64)blockIdx.y * TILE, b0 = (i64)blockIdx.x * TILE;
+  const i64 a0 = (i64)ta * TILE, b0 = (i64)tb * TILE;
   const i64 t_lo = P.tr_begin + (i64)blockIdx.z * P.tr_per_slice;
   const i64 t_hi = min(t_lo + P.tr_per_slice, P.tr_end);
+  if (threadIdx.x < TILE) {
+    dep_a[threadIdx.x] = (a0 + threadIdx.x < P.dim) ? deposit(a0 + threadIdx.x, P.keep_mask) : -1;
+    dep_b[threadIdx.x] = (b0 + threadIdx.x < P.dim) ? deposit(b0 + threadIdx.x, P.keep_mask) : -1;
+  }
 
-  double acc[2][2][2] = {};
+  double acc[4][4][2] = {};
   for (i64 t0 = t_lo; t0 < t_hi; t0 += KC) {
-    // 32 x KC amplitudes per operand, 4 per thread
+    __syncthreads();  // previous step's reads are done (and dep_a/dep_b are visible)
+    if (threadIdx.x < KC) dep_t[threadIdx.x] = (t0 + threadIdx.x < t_hi) ? deposit(t0 + threadIdx.x, P.tr_mask) : -1;
+    __syncthreads();
     for (int e = threadIdx.x; e < TILE * KC; e += 256) {
       const int row = e & (TILE - 1), kk = e / TILE;
-      const i64 tr = t0 + kk;
+      const i64 tr = dep_t[kk];
       cplx va = make_double2(0.0, 0.0), vb = va;
-      if (tr < t_hi) {
-        const i64 trbits = deposit(tr, P.tr_mask);
-        if (a0 + row < P.dim) va = amplitude(sub, P, trbits | deposit(a0 + row, P.keep_mask));
-        if (b0 + row < P.dim) vb = amplitude(sub, P, trbits | deposit(b0 + row, P.keep_mask));
+      if (tr >= 0) {
+        if (dep_a[row] >= 0) va = amplitude(sub, P, tr | dep_a[row]);
+        if (!diag_tile && dep_b[row] >= 0) vb = amplitude(sub, P, tr | dep_b[row]);
       }
       As[kk][row] = va;
-      Bs[kk][row] = vb;
+      if (!diag_tile) Bs[kk][row] = vb;
     }
     __syncthreads();
-#pragma unroll 8
+    const double2(*Bt)[TILE + 1] = diag_tile ? As : Bs;
+#pragma unroll 4
     for (int kk = 0; kk < KC; ++kk) {
-      const double2 av[2] = {As[kk][2 * ty], As[kk][2 * ty + 1]};
-      const double2 bv[2] = {Bs[kk][2 * tx], Bs[kk][2 * tx + 1]};
+      double2 av[4], bv[4];
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < 4; ++i) {
+        av[i] = As[kk][4 * ty + i];
+        bv[i] = Bt[kk][4 * tx + i];
+      }
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
           acc[i][j][0] += av[i].x * bv[j].x + av[i].y * bv[j].y;  // a * conj(b)
           acc[i][j][1] += av[i].y * bv[j].x - av[i].x * bv[j].y;
         }
     }
-    __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const i64 a = a0 + 2 * ty + i, b = b0 + 2 * tx + j;
+    for (int j = 0; j < 4; ++j) {
+      const i64 a = a0 + 4 * ty + i, b = b0 + 4 * tx + j;
       if (a < P.dim && b < P.dim) {
         atomicAdd(&rho[2 * (a * P.dim + b)], acc[i][j][0]);
         atomicAdd(&rho[2 * (a * P.dim + b) + 1], acc[i][j][1]);
       }
     }
+}
+
+// fill the tiles below the diagonal: rho[b][a] = conj(rho[a][b]) (32x32 shared-memory transpose)
+__global__ void __launch_bounds__(256) k_rdm_mirror(double2 *__restrict__ rho, i64 dim)
+{
+  __shared__ double2 t[32][33];
+  const i64 bx = blockIdx.x, by = blockIdx.y;  // 32x32 blocks; source block (by, bx) with bx's TILE > by's TILE
+  if ((bx * 32) / TILE <= (by * 32) / TILE) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const i64 a = by * 32 + r, b = bx * 32 + tx;
+    if (a < dim && b < dim) t[r][tx] = rho[a * dim + b];
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const i64 b = bx * 32 + r, a = by * 32 + tx;
+    if (a < dim && b < dim) {
+      const double2 v = t[tx][r];
+      rho[b * dim + a] = make_double2(v.x, -v.y);
+    }
+  }
 }
 
 }  // namespace
@@ -151,8 +192,10 @@ extern "C" int dnm_rdm(dnm_vec_t v, const dnm_subspace_t *sub, int64_t keep_size
   P.tr_begin = std::min(tr_dim, per_rank * G.rank);
   P.tr_end = std::min(tr_dim, P.tr_begin + per_rank);
   const i64 tiles = (P.dim + TILE - 1) / TILE;
+  P.ntiles = (int)tiles;
+  const i64 tile_pairs = tiles * (tiles + 1) / 2;
   const i64 span = P.tr_end - P.tr_begin;
-  i64 want_slices = std::max<i64>(1, ((i64)G.sm_count * 4) / (tiles * tiles));
+  i64 want_slices = std::max<i64>(1, ((i64)G.sm_count * 4) / tile_pairs);
   i64 slices = std::max<i64>(1, std::min<i64>(want_slices, (span + KC - 1) / KC));
   slices = std::min<i64>(slices, 65535);
   P.tr_per_slice = std::max<i64>(KC, ((span + slices - 1) / slices + KC - 1) / KC * KC);
@@ -166,7 +209,7 @@ extern "C" int dnm_rdm(dnm_vec_t v, const dnm_subspace_t *sub, int64_t keep_size
     DNM_CHECK_CUDA(cudaMemsetAsync(d_rho, 0, sizeof(double) * nout, G.stream));
     if (G.nranks > 1) allreduce_sum_dev(G.d_scratch + SCRATCH_DOUBLES - 8, 1);  // peers' vectors are complete
     if (span > 0) {
-      const dim3 grid((unsigned)tiles, (unsigned)tiles, (unsigned)slices);
+      const dim3 grid((unsigned)tile_pairs, 1, (unsigned)slices);
       switch (h.desc.type) {
         case DNM_FULL: k_rdm<<<grid, 256, 0, G.stream>>>(h.full(), P, d_rho); break;
         case DNM_PARITY: k_rdm<<<grid, 256, 0, G.stream>>>(h.parity(), P, d_rho); break;
@@ -179,6 +222,13 @@ extern "C" int dnm_rdm(dnm_vec_t v, const dnm_subspace_t *sub, int64_t keep_size
     if (G.nranks > 1) {
       DNM_REQUIRE(nout < ((size_t)1 << 31), DNM_ERR_UNSUPPORTED, "reduced density matrix too large to all-reduce");
       allreduce_sum_dev(d_rho, (int)nout);
+    }
+    if (P.dim > TILE) {
+      // tiles strictly below the diagonal were not computed
+      const unsigned nb = (unsigned)((P.dim + 31) / 32);
+      k_rdm_mirror<<<dim3(nb, nb), 256, 0, G.stream>>>(reinterpret_cast<double2 *>(d_rho), P.dim);
+      count_launch();
+      DNM_CHECK_CUDA(cudaGetLastError());
     }
     DNM_CHECK_CUDA(cudaMemcpyAsync(out, d_rho, sizeof(double) * nout, cudaMemcpyDeviceToHost, G.stream));
     DNM_CHECK_CUDA(cudaStreamSynchronize(G.stream));
