@@ -405,6 +405,9 @@ def run_ours(args, rank, world, local_rank):
                 'algorithmic_bytes_per_matmult': model_bytes,
                 'compulsory_bytes_per_matmult': compulsory,
                 'compulsory_gbs': compulsory / (sec / args.steps) / 1e9,
+                # what the memory system really moved (ncu dram bytes per MatMult, profiles/) over the same time
+                'dram_gbs': (traffic / (sec / args.steps) / 1e9) if traffic else None,
+                'dram_frac': (traffic / (sec / args.steps) / 1e9 / peak) if traffic else None,
                 'note': 'achieved uses the north-star model (unique_masks+1)*N*16 B per MatMult per GPU; the '
                         'tiled kernel moves far fewer bytes than the model, so frac > 1 is expected'}
 
