@@ -63,6 +63,15 @@ def main():
             y = H.dot(x)
             check(f'matmult {name} L={L} {kind} diag={diag}', rel_err(y.vec[a:b], want[a:b]) < 1e-12,
                   f'err={rel_err(y.vec[a:b], want[a:b]):.2e}')
+            # the other two ways of fetching remote amplitudes: NVLink peer loads inside the MatMult
+            # kernel, and the same on a side stream into a separate buffer
+            for mode in ('peer', 'peer_overlap', 'dma'):
+                os.environ['DNM_REMOTE'] = mode
+                H.get_mat().set_option('tile_bits', 0)      # drops the cached plan
+                y2 = H.dot(x)
+                check(f'matmult[{mode}] {name} L={L}', rel_err(y2.vec[a:b], want[a:b]) < 1e-12)
+            os.environ.pop('DNM_REMOTE', None)
+            H.get_mat().set_option('tile_bits', 0)
             nrm = H.infinity_norm()
             check(f'norm {name}', abs(nrm - oracle.norm_inf(omsc, osub, osub)) < 1e-12 * nrm)
             # global reductions

@@ -207,3 +207,32 @@ def test_spinconserve_rank_delta_random_masks(gpu):
             mat = product_mat(tlist, spec, spec, precompute_diag=diag)
             assert rel_err(device_mult(mat, x), want) < TOL, (L, k, diag)
             mat.destroy()
+
+
+def test_wide_states_beyond_32_bits(gpu):
+    """64-bit states end to end (reference tests/integration/test_matrices.py:183-232 uses L=33):
+    SpinConserve and Explicit subspaces of a 40-spin chain, column by column against the oracle."""
+    from dynamite_b200.hamiltonians import build_hamiltonian
+    L = 40
+    H = build_hamiltonian('heisenberg', L)
+    H.reduce_msc()
+    terms = [(int(m), int(s), complex(c)) for m, s, c in H.msc]
+    msc = oracle.Msc.from_terms(terms)
+    spec = {'type': 'spinconserve', 'L': L, 'k': 2}
+    sub = oracle.Subspace(spec)
+    assert sub.dim == 780
+    states = sub.i2s(np.arange(sub.dim))
+    R = np.random.RandomState(2)
+    shuffled = states.copy()
+    R.shuffle(shuffled)
+    for sp in (spec, {'type': 'explicit', 'L': L, 'states': states.tolist()},
+               {'type': 'explicit', 'L': L, 'states': shuffled.tolist()}):
+        osub = oracle.Subspace(sp)
+        mat = product_mat(terms, sp, sp)
+        for col in (0, 1, 389, 779):
+            e = np.zeros(osub.dim, complex)
+            e[col] = 1
+            assert np.allclose(device_mult(mat, e), oracle.matmult(msc, osub, osub, e), atol=1e-13)
+        x = rand_state(osub.dim, 3)
+        assert rel_err(device_mult(mat, x), oracle.matmult(msc, osub, osub, x)) < TOL
+        mat.destroy()
