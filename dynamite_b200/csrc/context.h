@@ -154,6 +154,7 @@ struct dnm_mat_s {
   int kernel_pref = 0;  // 0 auto, 1 general, 2 tiled
   int tile_bits = 0;    // 0 auto
   int tile_rows = 0;    // rows per thread in the tiled kernel: 0 auto, 8 or 16
+  int pipeline = 0;     // pipelined persistent tiled kernel: 0 auto, 1 on, 2 off
   int verbose = 0;
   dnm::TiledPlan *tiled = nullptr;
   int launches_per_mult = 0;

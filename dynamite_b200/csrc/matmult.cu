@@ -559,6 +559,10 @@ extern "C" int dnm_mat_set_option(dnm_mat_t A, const char *key, int64_t value)
     DNM_REQUIRE(value == 0 || value == 8 || value == 16, DNM_ERR_ARG, "tile_rows must be 0 (auto), 8 or 16");
     A->tile_rows = (int)value;
     tiled_free(A);
+  } else if (!strcmp(key, "pipeline")) {
+    DNM_REQUIRE(value >= 0 && value <= 2, DNM_ERR_ARG, "pipeline must be 0 (auto), 1 (on) or 2 (off)");
+    A->pipeline = (int)value;
+    tiled_free(A);
   } else if (!strcmp(key, "verbose")) {
     A->verbose = (int)value;
   } else {

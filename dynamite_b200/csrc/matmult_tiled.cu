@@ -173,6 +173,7 @@ struct Pass {
   int T = 0;
   int R = 16;
   int peer_xor = 0;  // x is read from rank ^ peer_xor
+  bool pipe = false; // run with the pipelined persistent kernel (k_tiled_ring)
   int nterms = 0;
   int nmasks = 0;
   i64 wbits = 0;     // window bit positions
@@ -334,6 +335,25 @@ Direct make_direct(const std::vector<const NMask *> &masks, int nloc, int accumu
   return d;
 }
 
+// runs of consecutive outer positions, for tile_outer_bits
+void fill_segments(PassParams &p)
+{
+  p.n_seg = 0;
+  int k = 0;
+  while (k < p.n_outer) {
+    int e = k + 1;
+    while (e < p.n_outer && p.outer_pos[e] == p.outer_pos[e - 1] + 1) ++e;
+    if (p.n_seg == MAX_SEGS) {
+      p.n_seg = -1;
+      return;
+    }
+    p.seg_mask[p.n_seg] = (((unsigned long long)1 << (e - k)) - 1ull) << k;
+    p.seg_shift[p.n_seg] = (unsigned char)(p.outer_pos[k] - k);
+    ++p.n_seg;
+    k = e;
+  }
+}
+
 Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &W, int T, int R, int B, int nloc,
                int accumulate)
 {
@@ -364,7 +384,7 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
   // row bits come first
   std::vector<u32> lam, sw, rb, toff;
   std::vector<u16> t0, t1, t2, pat;
-  std::vector<u8> kp;
+  std::vector<u8> kp, role;
   std::vector<i64> so;
   std::vector<double> cf, tabs;
   std::vector<unsigned long long> rpat;
@@ -379,6 +399,10 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
   }
   const bool allow_tables = R <= 8 && !(general_groups <= (size_t)SMALL_GROUPS && general_terms <= (size_t)SMALL_TERMS) &&
                             getenv("DNM_NO_TABLES") == nullptr;
+  // small passes (tables in kernel-parameter memory) use the lean PATH_PAIR encoding wherever a
+  // group has at most two distinct sign masks; it may add one padding entry per group
+  const bool small_pass = general_groups <= (size_t)SMALL_GROUPS && general_terms + general_groups <= (size_t)SMALL_TERMS &&
+                          getenv("DNM_NO_PAIR") == nullptr;
   bool any_table = false;
   for (const NMask *nm : masks) {
     const u32 l = extract(nm->mask & lmask);
@@ -392,6 +416,49 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
       lam.push_back(l);
       toff.push_back(0);
       rpat.push_back(0);
+      if (small_pass) {
+        // distinct sign masks of the group, coefficients of equal masks summed
+        std::vector<std::pair<i64, double>> uniq;
+        for (const NTerm &t : nm->terms) {
+          if ((int)t.imag != kind) continue;
+          bool found = false;
+          for (auto &u : uniq)
+            if (u.first == t.sign) {
+              u.second += t.coef;
+              found = true;
+            }
+          if (!found) uniq.emplace_back(t.sign, t.coef);
+        }
+        if (uniq.size() <= 2) {
+          role.resize(sw.size(), 0);  // entries of earlier, ordinary groups
+          if (sw.size() & 1) {  // the (c1+c2, c1-c2) scratch pair is read as one 16-byte word
+            sw.push_back(0);
+            rb.push_back(0);
+            so.push_back(0);
+            cf.push_back(0.0);
+            role.push_back(0);
+          }
+          if (uniq.size() == 1) uniq.emplace_back(uniq[0].first, 0.0);
+          const i64 s1 = uniq[0].first, s2 = uniq[1].first;
+          t0.push_back((u16)sw.size());
+          const u32 wa = extract(s1 & lmask), wb = extract((s1 ^ s2) & lmask);
+          sw.push_back(wa);
+          rb.push_back(row_pattern(wa));
+          so.push_back(s1 & ~wbits);
+          cf.push_back(uniq[0].second);
+          role.push_back(1);
+          sw.push_back(wb);
+          rb.push_back(row_pattern(wb));
+          so.push_back(s2 & ~wbits);
+          cf.push_back(uniq[1].second);
+          role.push_back(2);
+          t1.push_back((u16)sw.size());
+          t2.push_back((u16)sw.size());
+          pat.push_back(0);
+          kp.push_back((u8)(kind | (PATH_PAIR << 1)));
+          continue;
+        }
+      }
       t0.push_back((u16)sw.size());
       if (allow_tables && plain.size() + rowdep.size() >= 4) {
         // GF(2) basis of the sign masks; coords[t] = which basis vectors XOR to term t's mask
@@ -491,6 +558,7 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
       if ((h >> (b - B)) & 1) off |= (i64)1 << W[b];
     rowoff[h] = off;
   }
+  role.resize(sw.size(), 0);
   ps.p.ngroups = (int)lam.size();
   ps.p.nterms = (int)sw.size();
   ps.p.B = B;
@@ -498,6 +566,7 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
   ps.p.n_outer = 0;
   for (int b = 0; b < nloc; ++b)
     if (!((wbits >> b) & 1)) ps.p.outer_pos[ps.p.n_outer++] = (unsigned char)b;
+  fill_segments(ps.p);
   ps.p.lam = up(lam, ps.owned);
   ps.p.t0 = up(t0, ps.owned);
   ps.p.t1 = up(t1, ps.owned);
@@ -536,7 +605,16 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
       ps.st.rb[t] = rb[t];
       ps.st.so[t] = so[t];
       ps.st.cf[t] = cf[t];
+      ps.st.role[t] = role[t];
     }
+    bool lean = R <= 8;
+    for (int g = 0; g < ps.p.ngroups && lean; ++g) lean = (kp[g] >> 1) == PATH_PAIR && t0[g] == 2 * g;
+    if (lean)
+      for (int g = 0; g < ps.p.ngroups; ++g)
+        ps.st.gd[g] = make_uint4(lam[g], sw[2 * g], sw[2 * g + 1],
+                                 (rb[2 * g] & 0xffu) | ((rb[2 * g + 1] & 0xffu) << 8) | ((u32)(kp[g] & 1) << 16));
+    ps.p.lean = lean ? 1 : 0;
+    if (const char *e = getenv("DNM_RING_DEBUG")) ps.p.debug = atoi(e);
   }
   return ps;
 }
@@ -644,6 +722,85 @@ void launch_tiled(const Pass &ps, const cplx *x, cplx *y, const double *diag, i6
   else launch_tiled_v<T, R, false>(ps, x, y, diag, ntiles);
 }
 
+// ---- pipelined persistent kernel (k_tiled_ring) ----
+// shared memory left for staged term tables next to the three half-tile buffers
+template <int T>
+constexpr size_t pipe_table_room()
+{
+  // per CTA: 1 KiB reserved by the system, ~1 KiB of static shared memory; at most 227 KiB per block
+  constexpr long long share = 233472 / RingCfg<T>::CTAS;
+  constexpr long long cap = share < 232448 ? share : 232448;
+  constexpr long long room = cap - 2048 - (long long)RingCfg<T>::RING_BYTES;
+  return room > 0 ? (size_t)room : 0;
+}
+
+size_t pipe_room(int T)
+{
+  switch (T) {
+    case 10: return pipe_table_room<10>();
+    case 11: return pipe_table_room<11>();
+    case 12: return pipe_table_room<12>();
+    case 13: return pipe_table_room<13>();
+    default: return 0;
+  }
+}
+
+bool pipe_eligible(const Pass &ps)
+{
+  return ps.R == 8 && ps.T >= 10 && ps.T <= 13 && ps.p.accumulate != 2 &&
+         (!ps.p.staged || (size_t)ps.nterms * 16 <= pipe_room(ps.T));
+}
+
+// work tickets of the persistent kernels: a small ring so that launches on different streams
+// never share a counter
+unsigned long long *next_ticket(cudaStream_t st)
+{
+  static unsigned long long *d_tickets = nullptr;
+  static int cursor = 0;
+  constexpr int N = 64;
+  if (!d_tickets) DNM_CHECK_CUDA(cudaMalloc(&d_tickets, N * sizeof(unsigned long long)));
+  unsigned long long *t = d_tickets + (cursor++ % N);
+  DNM_CHECK_CUDA(cudaMemsetAsync(t, 0, sizeof(unsigned long long), st));
+  return t;
+}
+
+template <int T, bool SMALL>
+void launch_pipe_v(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
+{
+  static bool attr_set = false;
+  const size_t smem = RingCfg<T>::RING_BYTES + (ps.p.staged ? (size_t)ps.nterms * 16 : 0);
+  if (!attr_set) {
+    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_ring<T, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(RingCfg<T>::RING_BYTES + pipe_table_room<T>())));
+    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_ring<T, SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_set = true;
+  }
+  i64 grid = std::min<i64>(ntiles, (i64)G.sm_count * RingCfg<T>::CTAS);
+  if (const char *e = getenv("DNM_PIPE_CTAS"))  // tests: few CTAs, many tiles each
+    if (atoi(e) > 0) grid = std::min<i64>(grid, atoi(e));
+  cudaStream_t st = launch_stream();
+  unsigned long long *ticket = next_ticket(st);
+  k_tiled_ring<T, SMALL><<<(unsigned)grid, RingCfg<T>::NT, smem, st>>>(ps.p, ps.st, x, y, diag, (unsigned long long)ntiles,
+                                                                    ticket);
+  count_launch();
+  DNM_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_pipe(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
+{
+#define DNM_PIPE_CASE(TT)                                                      \
+  if (ps.T == TT) {                                                            \
+    if (ps.small) return launch_pipe_v<TT, true>(ps, x, y, diag, ntiles);      \
+    return launch_pipe_v<TT, false>(ps, x, y, diag, ntiles);                   \
+  }
+  DNM_PIPE_CASE(10)
+  DNM_PIPE_CASE(11)
+  DNM_PIPE_CASE(12)
+  DNM_PIPE_CASE(13)
+#undef DNM_PIPE_CASE
+  DNM_REQUIRE(false, DNM_ERR_INTERNAL, "no pipelined kernel for T=%d", ps.T);
+}
+
 // rows per thread for a tile size: 16 by default (8 on request) where the CTA stays >= 64 threads
 int rows_for(int T, int want)
 {
@@ -654,6 +811,7 @@ int rows_for(int T, int want)
 
 void launch_pass(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
 {
+  if (ps.pipe) return launch_pipe(ps, x, y, diag, ntiles);
 #define DNM_TILE_CASE(TT, RR) \
   if (ps.T == TT && ps.R == RR) return launch_tiled<TT, RR>(ps, x, y, diag, ntiles);
   DNM_TILE_CASE(8, 4)
@@ -804,6 +962,7 @@ void build_units(TiledPlan &plan, int verbose)
         for (int b = 0; b < nloc; ++b)
           if (!((U >> b) & 1)) fp.p[k].outer_pos[pos++] = (unsigned char)b;
         fp.p[k].n_outer = pos;
+        fill_segments(fp.p[k]);
         if (plan.use_diag && u.passes[k] == 0) fp.diag_pass = k;
       }
       const size_t nflags = (size_t)(fp.npasses - 1) * (size_t)fp.nchunks;
@@ -881,6 +1040,10 @@ std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &mas
   }
   // cost in vector sweeps over HBM: a writing pass reads x and writes y (2), an
   // accumulating pass also re-reads y (3); a direct gather re-reads x once per mask.
+  // pipeline: 1 = the ring kernel wherever it exists; 0 (auto) and 2 = one tile per CTA.  Measured on
+  // B200 (profiles/r01_ring_experiment.md): the arithmetic phase is bound by shared-memory
+  // bandwidth, not by the fetches the ring hides, and the ring kernel is 5-20 % slower.
+  for (Pass &ps : plan->passes) ps.pipe = A->pipeline == 1 && pipe_eligible(ps);
   build_units(*plan, verbose);
   double cost = 0.0;
   for (const Unit &u : plan->units) {
@@ -903,11 +1066,11 @@ TiledPlan *build_plan(dnm_mat_s *A)
 
   std::vector<std::pair<int, int>> candidates;  // (T, B)
   const char *env_b = getenv("DNM_TILE_RUN_BITS");
-  // Measured on B200 (profiles/explore_r01.md): up to 2^28 rows per GPU 64 KB tiles (T=12) win;
-  // beyond that the passes over the highest bits touch hundreds of 2 MB pages per tile and
-  // 32 KB tiles (T=11, more CTAs per SM, one more pass) are faster.
+  // Measured on B200 (profiles/r01_explore_tiles.log, r01_ring_experiment.md): up to 2^28 rows per
+  // GPU 64 KB tiles (T=12, two CTAs per SM) win; beyond that 128 KB tiles (T=13, one pass fewer
+  // over HBM) do -- 64 KB tiles would need 64-byte runs there, which thrash at 16 MB strides.
   std::vector<int> Ts = A->tile_bits ? std::vector<int>{A->tile_bits}
-                                     : (nloc >= 29 ? std::vector<int>{11} : std::vector<int>{12});
+                                     : (nloc >= 29 ? std::vector<int>{13} : std::vector<int>{12});
   std::vector<int> Bs = env_b ? std::vector<int>{atoi(env_b)} : std::vector<int>{3, 2};
   for (int T : Ts)
     for (int B : Bs) {

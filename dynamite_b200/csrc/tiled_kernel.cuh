@@ -28,7 +28,9 @@ typedef unsigned char u8;
 constexpr int SMALL_GROUPS = 48;  // passes up to this size keep their tables in kernel-parameter
 constexpr int SMALL_TERMS = 96;   // (constant) memory; bigger ones read them from global memory
 
-enum { PATH_SCALAR = 0, PATH_TWO = 1, PATH_GENERAL = 2, PATH_TABLE = 3 };
+constexpr int MAX_SEGS = 12;
+
+enum { PATH_SCALAR = 0, PATH_TWO = 1, PATH_GENERAL = 2, PATH_TABLE = 3, PATH_PAIR = 4 };
 
 struct PassParams {
   int ngroups;
@@ -43,7 +45,13 @@ struct PassParams {
   const u16 *t1;   // first term with r bits
   const u16 *t2;   // one past the last term
   const u16 *pat;  // PATH_TWO: bit r = sign of the r-dependent terms on row group r
-  const u8 *kp;    // bit 0: imaginary coefficients, bits 1..2: path
+  const u8 *kp;    // bit 0: imaginary coefficients, bits 1..3: path
+  // PATH_PAIR groups (at most two distinct sign masks s1, s2 -- every nearest-neighbour model):
+  //   D(l) = sigma(s1 & l) * (c1 + c2 * sigma((s1^s2) & l)),   sigma(v) = (-1)^popcount(v)
+  // stored as two "terms" at an even index t0: sw/rb hold the window bits / row patterns of s1 and
+  // of s1^s2, so/cf the outside-window bits and coefficients of the two terms; per tile the
+  // scratch holds (c1' + c2', c1' - c2') with the tile-uniform signs folded in.
+
   // PATH_TABLE groups (many terms per mask): the terms' sign masks span a GF(2) space of dimension
   // d <= 6; the group's "terms" t0..t1 are the d basis vectors and the coefficient of a row is
   // tabs[toff + index], index bit k = parity(basis_k & row)
@@ -59,6 +67,15 @@ struct PassParams {
   i64 rank_bits;      // global index bits contributed by the rank
   i64 roff[16];       // offset contributed by the r-th row group of a thread
   unsigned char outer_pos[48];
+  // the same deposit as runs of consecutive positions: outer = OR_j (tile_id & seg_mask[j]) << seg_shift[j]
+  // (n_seg < 0: too many runs, use outer_pos bit by bit)
+  int n_seg;
+  unsigned char seg_shift[MAX_SEGS];
+  unsigned long long seg_mask[MAX_SEGS];
+  // every group is a PATH_PAIR group at t0 = 2g with row patterns of at most 8 bits: the kernels
+  // run the lean group loop on SmallTables::gd
+  int lean;
+  int debug;  // timing experiments only (DNM_RING_DEBUG): bit 0 skip the arithmetic, bit 1 skip the x fetches, bit 2 skip old y
 };
 
 // the same tables by value, for small passes (terms indices fit u8)
@@ -70,6 +87,10 @@ struct SmallTables {
   u32 rb[SMALL_TERMS];
   i64 so[SMALL_TERMS];
   double cf[SMALL_TERMS];
+  u8 role[SMALL_TERMS];  // 0: ordinary term, 1 / 2: first / second entry of a PATH_PAIR group
+  // lean passes: one 16-byte descriptor per group
+  //   x = lam, y = window bits of s1, z = window bits of s1^s2, w = pat(s1) | pat(s1^s2) << 8 | imag << 16
+  uint4 gd[SMALL_GROUPS];
 };
 
 constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v / 2); }
@@ -105,16 +126,29 @@ __device__ __forceinline__ void cp_async_wait_all()
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-// acc[r] += (IMAG ? i*d_r : d_r) * tile[(r ^ HI) rows, column `base`]: HI is a template
-// parameter so every LDS has an immediate offset and there is no per-row address arithmetic.
-template <int R, int LOG_NT, int HI, bool IMAG, bool SCALAR>
-__device__ __forceinline__ void gather_fixed(double (&ar)[R], double (&ai)[R], const double2 *col, double d0,
-                                             const double (&d)[R])
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// acc[r] += (IMAG ? i*d_r : d_r) * (row r ^ HI of the tile, this thread's partner column `col`).
+// HI is a template parameter, so in a contiguous tile every LDS has an immediate offset and there
+// is no per-row address arithmetic.  RING (ring kernel): rows live in pairs (quarters of the
+// tile) at element offsets qoff[0..R/2) of the ring buffer.
+template <int R, int LOG_NT, int HI, bool IMAG, bool SCALAR, bool RING>
+__device__ __forceinline__ void gather_fixed(double (&ar)[R], double (&ai)[R], const double2 *col, const int *qoff,
+                                             double d0, const double (&d)[R])
 {
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const double2 v = col[(r ^ HI) << LOG_NT];
     const double c = SCALAR ? d0 : d[r];
+    // rows with a zero coefficient (flip-flop terms: half of them) are not fetched; shared-memory
+    // bandwidth is what bounds the arithmetic phase
+    if (!SCALAR && c == 0.0) continue;
+    const double2 v = RING ? col[qoff[(r ^ HI) >> 1] + (((r ^ HI) & 1) << LOG_NT)] : col[(r ^ HI) << LOG_NT];
     if (IMAG) {
       ar[r] -= c * v.y;
       ai[r] += c * v.x;
@@ -125,13 +159,13 @@ __device__ __forceinline__ void gather_fixed(double (&ar)[R], double (&ai)[R], c
   }
 }
 
-template <int R, int LOG_NT, bool IMAG, bool SCALAR>
-__device__ __forceinline__ void gather_switch(double (&ar)[R], double (&ai)[R], const double2 *col, int hi_l, double d0,
-                                              const double (&d)[R])
+template <int R, int LOG_NT, bool IMAG, bool SCALAR, bool RING>
+__device__ __forceinline__ void gather_switch(double (&ar)[R], double (&ai)[R], const double2 *col, const int *qoff,
+                                              int hi_l, double d0, const double (&d)[R])
 {
 #define DNM_HI_CASE(H) \
   case H:               \
-    if (H < R) gather_fixed<R, LOG_NT, (H < R ? H : 0), IMAG, SCALAR>(ar, ai, col, d0, d); \
+    if (H < R) gather_fixed<R, LOG_NT, (H < R ? H : 0), IMAG, SCALAR, RING>(ar, ai, col, qoff, d0, d); \
     break;
   switch (hi_l) {
     DNM_HI_CASE(0) DNM_HI_CASE(1) DNM_HI_CASE(2) DNM_HI_CASE(3) DNM_HI_CASE(4) DNM_HI_CASE(5) DNM_HI_CASE(6)
@@ -147,7 +181,11 @@ __device__ __forceinline__ void gather_switch(double (&ar)[R], double (&ai)[R], 
 __device__ __forceinline__ i64 tile_outer_bits(const PassParams &P, unsigned long long tile_id)
 {
   i64 g = 0;
-  for (int k = 0; k < P.n_outer; ++k) g |= (i64)((tile_id >> k) & 1ull) << P.outer_pos[k];
+  if (P.n_seg >= 0) {
+    for (int j = 0; j < P.n_seg; ++j) g |= (i64)((tile_id & P.seg_mask[j]) << P.seg_shift[j]);
+  } else {
+    for (int k = 0; k < P.n_outer; ++k) g |= (i64)((tile_id >> k) & 1ull) << P.outer_pos[k];
+  }
   return g;
 }
 
@@ -168,24 +206,25 @@ __device__ __forceinline__ void prefetch_tile_l2(const PassParams &P, const cplx
   }
 }
 
-template <int T, int R, bool SMALL>
-__device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables &S, i64 outer, i64 base_g,
-                                          const cplx *__restrict__ x, cplx *__restrict__ y,
-                                          const double *__restrict__ diag, double2 *tile, double *csign)
+// Per-tile coefficient scratch: every term's coefficient with the tile-uniform sign applied (and,
+// for staged passes, the window sign bits) -- written once per tile, read by every thread.
+template <int NT, bool SMALL>
+__device__ __forceinline__ void stage_tables(const PassParams &P, const SmallTables &S, i64 outer_g, double *csign)
 {
-  constexpr int NT = TileCfg<T, R>::NT;
-  constexpr int LOG_NT = TileCfg<T, R>::LOG_NT;
   const int tid = threadIdx.x;
-  const i64 outer_g = outer | P.rank_bits;  // sign-relevant bits shared by the whole tile
-
-  // stage the tile: runs of 2^B contiguous amplitudes, asynchronous 16-byte copies
-#pragma unroll
-  for (int r = 0; r < R; ++r) cp_async16(&tile[tid + r * NT], &x[base_g | P.roff[r]]);
   uint2 *swrb = reinterpret_cast<uint2 *>(csign + P.nterms);  // staged passes only
   if (SMALL) {
-    // coefficient with the tile-uniform sign applied, once per tile
-    for (int t = tid; t < P.nterms; t += NT)
-      csign[t] = flip_sign(S.cf[t], __popcll((unsigned long long)(S.so[t] & outer_g)) & 1);
+    for (int t = tid; t < P.nterms; t += NT) {
+      const int role = S.role[t];
+      const double c = flip_sign(S.cf[t], __popcll((unsigned long long)(S.so[t] & outer_g)) & 1);
+      if (role == 0) {
+        csign[t] = c;
+      } else {  // (c1 + c2, c1 - c2) of a pair group
+        const int u = (role == 1) ? t + 1 : t - 1;
+        const double o = flip_sign(S.cf[u], __popcll((unsigned long long)(S.so[u] & outer_g)) & 1);
+        csign[t] = (role == 1) ? c + o : o - c;
+      }
+    }
   } else if (P.staged) {
     // many-term passes (SYK): the same, plus the window sign bits, staged once per tile so the
     // per-thread term loop reads shared memory instead of four global tables
@@ -194,22 +233,81 @@ __device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables
       swrb[t] = make_uint2(__ldg(&P.sw[t]), __ldg(&P.rb[t]));
     }
   }
+}
+
+// Stage one tile of x in shared memory (asynchronous 16-byte copies, runs of 2^B amplitudes) and
+// the per-tile coefficient scratch; returns after the data is visible to the whole CTA.
+template <int NT, int R, bool SMALL>
+__device__ __forceinline__ void stage_tile(const PassParams &P, const SmallTables &S, i64 outer_g, i64 base_g,
+                                           const cplx *__restrict__ x, double2 *tile, double *csign)
+{
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int r = 0; r < R; ++r) cp_async16(&tile[tid + r * NT], &x[base_g | P.roff[r]]);
+  stage_tables<NT, SMALL>(P, S, outer_g, csign);
   cp_async_wait_all();
   __syncthreads();
+}
 
-  double ar[R], ai[R];
-  if (diag != nullptr) {
+// The lean group loop (P.lean): every group has at most two distinct sign masks, so
+//   D(l) = sigma(s1 & l) * (c1 + c2 * sigma((s1^s2) & l))
+// and a group costs one 16-byte descriptor (kernel-parameter memory, uniform), one 16-byte
+// scratch read (c1+c2, c1-c2 with the tile signs folded in), two popcounts and the gather.
+template <int R, int LOG_NT, bool RING>
+__device__ __forceinline__ void process_groups_lean(const PassParams &P, const SmallTables &S, const double2 *tile,
+                                                    const double *csign, double (&ar)[R], double (&ai)[R],
+                                                    const int *qoff)
+{
+  constexpr int NT = 1 << LOG_NT;
+  const int tid = threadIdx.x;
+  const double2 *cpm = reinterpret_cast<const double2 *>(csign);
+#pragma unroll 1
+  for (int g = 0; g < P.ngroups; ++g) {
+    const uint4 gd = S.gd[g];
+    const double2 cc = cpm[g];
+    const double2 *col = tile + (tid ^ (int)(gd.x & (NT - 1)));
+    const int hi = (int)(gd.x >> LOG_NT);
+    const int pa = __popc(gd.y & (u32)tid) & 1, pb = __popc(gd.z & (u32)tid) & 1;
+    const bool imag = (gd.w >> 16) != 0;
+    if ((gd.w & 0xffffu) == 0) {
+      const double c = flip_sign(pb ? cc.y : cc.x, pa);
+      if (c != 0.0) {
+        const double none[R] = {};
+        if (imag) gather_switch<R, LOG_NT, true, true, RING>(ar, ai, col, qoff, hi, c, none);
+        else gather_switch<R, LOG_NT, false, true, RING>(ar, ai, col, qoff, hi, c, none);
+      }
+    } else {
+      const u32 qa = (gd.w & 0xffu) ^ (0u - (u32)pa), qb = ((gd.w >> 8) & 0xffu) ^ (0u - (u32)pb);
+      double d[R];
+      bool any = false;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const double d = __ldg(&diag[base_g | P.roff[r]]);
-      const double2 v = tile[tid + r * NT];
-      ar[r] = d * v.x;
-      ai[r] = d * v.y;
+      for (int r = 0; r < R; ++r) {
+        const double c = ((qb >> r) & 1u) ? cc.y : cc.x;
+        d[r] = flip_if(__double2hiint(c), __double2loint(c), qa, r);
+        any = any || (c != 0.0);
+      }
+      if (any) {
+        if (imag) gather_switch<R, LOG_NT, true, false, RING>(ar, ai, col, qoff, hi, 0.0, d);
+        else gather_switch<R, LOG_NT, false, false, RING>(ar, ai, col, qoff, hi, 0.0, d);
+      }
     }
-  } else {
-#pragma unroll
-    for (int r = 0; r < R; ++r) ar[r] = ai[r] = 0.0;
   }
+}
+
+// Accumulate every group of the pass into this thread's R rows  l = tid + r*NT.
+// Contiguous tile: `tile` is the 2^T-entry buffer.  RING mode (ring kernel): the tile is four
+// quarters (row pairs) at element offsets qoff[0..3] of `tile`.
+template <int R, int LOG_NT, bool SMALL, bool RING = false>
+__device__ __forceinline__ void process_groups(const PassParams &P, const SmallTables &S, const double2 *tile,
+                                               const double *csign, i64 outer_g, double (&ar)[R], double (&ai)[R],
+                                               const int *qoff = nullptr)
+{
+  if (SMALL && R <= 8 && P.lean) return process_groups_lean<R, LOG_NT, RING>(P, S, tile, csign, ar, ai, qoff);
+  constexpr int NT = 1 << LOG_NT;
+  constexpr int rbase = 0;
+  constexpr int RH = R;
+  const int tid = threadIdx.x;
+  const uint2 *swrb = reinterpret_cast<const uint2 *>(csign + P.nterms);  // staged passes only
 
   // coefficient of term t with tile and thread signs applied
   auto term = [&](int t) -> double {
@@ -225,33 +323,76 @@ __device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables
     const int base = tid ^ (int)(lam & (NT - 1));
     const int hi_l = (int)(lam >> LOG_NT);
     const int t0 = SMALL ? (int)S.t0[g] : (int)__ldg(&P.t0[g]);
-    const int t1 = SMALL ? (int)S.t1[g] : (int)__ldg(&P.t1[g]);
-    const int t2 = SMALL ? (int)S.t2[g] : (int)__ldg(&P.t2[g]);
     const int kp = SMALL ? (int)S.kp[g] : (int)__ldg(&P.kp[g]);
     const bool imag = kp & 1;
     const int path = kp >> 1;
+    // row r gathers from row (r ^ hi_l) of column `base`
+    const double2 *col = tile + base;
+    const int hi_lo = hi_l;
 
+    if (path == PATH_PAIR) {
+      // the lean path: no term loops, one 16-byte scratch read, two popcounts
+      const u32 swa = SMALL ? S.sw[t0] : __ldg(&P.sw[t0]);
+      const u32 swb = SMALL ? S.sw[t0 + 1] : __ldg(&P.sw[t0 + 1]);
+      const u32 pata = ((SMALL ? S.rb[t0] : __ldg(&P.rb[t0])) >> rbase) & ((1u << RH) - 1);
+      const u32 patb = ((SMALL ? S.rb[t0 + 1] : __ldg(&P.rb[t0 + 1])) >> rbase) & ((1u << RH) - 1);
+      double2 cc;  // (c1 + c2, c1 - c2), tile signs applied
+      if (SMALL) {
+        cc = *reinterpret_cast<const double2 *>(csign + t0);
+      } else {
+        const double c1 = flip_sign(__ldg(&P.cf[t0]), __popcll((unsigned long long)(__ldg(&P.so[t0]) & outer_g)) & 1);
+        const double c2 =
+            flip_sign(__ldg(&P.cf[t0 + 1]), __popcll((unsigned long long)(__ldg(&P.so[t0 + 1]) & outer_g)) & 1);
+        cc = make_double2(c1 + c2, c1 - c2);
+      }
+      const int pa = __popc(swa & (u32)tid) & 1, pb = __popc(swb & (u32)tid) & 1;
+      if ((pata | patb) == 0) {
+        const double c = flip_sign(pb ? cc.y : cc.x, pa);
+        if (c != 0.0) {
+          const double none[RH] = {};
+          if (imag) gather_switch<RH, LOG_NT, true, true, RING>(ar, ai, col, qoff, hi_lo, c, none);
+          else gather_switch<RH, LOG_NT, false, true, RING>(ar, ai, col, qoff, hi_lo, c, none);
+        }
+      } else {
+        const u32 qa = pata ^ (0u - (u32)pa), qb = patb ^ (0u - (u32)pb);
+        double d[RH];
+        bool any = false;
+#pragma unroll
+        for (int r = 0; r < RH; ++r) {
+          const double c = ((qb >> r) & 1u) ? cc.y : cc.x;
+          d[r] = flip_if(__double2hiint(c), __double2loint(c), qa, r);
+          any = any || (c != 0.0);
+        }
+        if (any) {
+          if (imag) gather_switch<RH, LOG_NT, true, false, RING>(ar, ai, col, qoff, hi_lo, 0.0, d);
+          else gather_switch<RH, LOG_NT, false, false, RING>(ar, ai, col, qoff, hi_lo, 0.0, d);
+        }
+      }
+      continue;
+    }
+
+    const int t1 = SMALL ? (int)S.t1[g] : (int)__ldg(&P.t1[g]);
+    const int t2 = SMALL ? (int)S.t2[g] : (int)__ldg(&P.t2[g]);
     double c0 = 0.0;  // terms without r bits: one scalar per thread
     if (SMALL || path != PATH_TABLE)
       for (int t = t0; t < t1; ++t) c0 += term(t);
 
-    const double2 *col = tile + base;
     if (path == PATH_SCALAR) {
       if (c0 != 0.0) {
-        const double none[R] = {};
-        if (imag) gather_switch<R, LOG_NT, true, true>(ar, ai, col, hi_l, c0, none);
-        else gather_switch<R, LOG_NT, false, true>(ar, ai, col, hi_l, c0, none);
+        const double none[RH] = {};
+        if (imag) gather_switch<RH, LOG_NT, true, true, RING>(ar, ai, col, qoff, hi_lo, c0, none);
+        else gather_switch<RH, LOG_NT, false, true, RING>(ar, ai, col, qoff, hi_lo, c0, none);
       }
     } else {
-      double d[R];
+      double d[RH];
       bool any;
       if (path == PATH_TWO) {
         double ch = 0.0;  // terms sharing the single r pattern `pat`
         for (int t = t1; t < t2; ++t) ch += term(t);
-        const u32 pat = SMALL ? (u32)S.pat[g] : (u32)__ldg(&P.pat[g]);
+        const u32 pat = (SMALL ? (u32)S.pat[g] : (u32)__ldg(&P.pat[g])) >> rbase;
         const double dp = c0 + ch, dm = c0 - ch;
 #pragma unroll
-        for (int r = 0; r < R; ++r) d[r] = ((pat >> r) & 1u) ? dm : dp;
+        for (int r = 0; r < RH; ++r) d[r] = ((pat >> r) & 1u) ? dm : dp;
         any = (dp != 0.0) || (dm != 0.0);
       } else if (!SMALL && path == PATH_TABLE) {
         // index of this thread's rows into the group's coefficient table: one parity per basis vector
@@ -266,30 +407,59 @@ __device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables
         const double *tab = P.tabs + __ldg(&P.toff[g]);
         any = false;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          d[r] = __ldg(&tab[q ^ (u32)((rp >> (8 * (r & 7))) & 0xffull)]);
+        for (int r = 0; r < RH; ++r) {
+          d[r] = __ldg(&tab[q ^ (u32)((rp >> (8 * ((rbase + r) & 7))) & 0xffull)]);
           any = any || (d[r] != 0.0);
         }
       } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r) d[r] = c0;
+        for (int r = 0; r < RH; ++r) d[r] = c0;
         for (int t = t1; t < t2; ++t) {
           const double c = term(t);
-          const u32 bits = SMALL ? S.rb[t] : (P.staged ? swrb[t].y : __ldg(&P.rb[t]));
+          const u32 bits = (SMALL ? S.rb[t] : (P.staged ? swrb[t].y : __ldg(&P.rb[t]))) >> rbase;
           const int chi = __double2hiint(c), clo = __double2loint(c);
 #pragma unroll
-          for (int r = 0; r < R; ++r) d[r] += flip_if(chi, clo, bits, r);
+          for (int r = 0; r < RH; ++r) d[r] += flip_if(chi, clo, bits, r);
         }
         any = false;
 #pragma unroll
-        for (int r = 0; r < R; ++r) any = any || (d[r] != 0.0);
+        for (int r = 0; r < RH; ++r) any = any || (d[r] != 0.0);
       }
       if (any) {
-        if (imag) gather_switch<R, LOG_NT, true, false>(ar, ai, col, hi_l, 0.0, d);
-        else gather_switch<R, LOG_NT, false, false>(ar, ai, col, hi_l, 0.0, d);
+        if (imag) gather_switch<RH, LOG_NT, true, false, RING>(ar, ai, col, qoff, hi_lo, 0.0, d);
+        else gather_switch<RH, LOG_NT, false, false, RING>(ar, ai, col, qoff, hi_lo, 0.0, d);
       }
     }
   }
+}
+
+// One tile of one pass.  `tile` is the CTA's 2^T-entry shared buffer, `csign` its per-term scratch.
+template <int T, int R, bool SMALL>
+__device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables &S, i64 outer, i64 base_g,
+                                          const cplx *__restrict__ x, cplx *__restrict__ y,
+                                          const double *__restrict__ diag, double2 *tile, double *csign)
+{
+  constexpr int NT = TileCfg<T, R>::NT;
+  constexpr int LOG_NT = TileCfg<T, R>::LOG_NT;
+  const int tid = threadIdx.x;
+  const i64 outer_g = outer | P.rank_bits;  // sign-relevant bits shared by the whole tile
+  stage_tile<NT, R, SMALL>(P, S, outer_g, base_g, x, tile, csign);
+
+  double ar[R], ai[R];
+  if (diag != nullptr) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double d = __ldg(&diag[base_g | P.roff[r]]);
+      const double2 v = tile[tid + r * NT];
+      ar[r] = d * v.x;
+      ai[r] = d * v.y;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) ar[r] = ai[r] = 0.0;
+  }
+
+  process_groups<R, LOG_NT, SMALL>(P, S, tile, csign, outer_g, ar, ai);
 
   if (P.accumulate == 2) {
     // passes of a small problem run concurrently in one grid: combine in the L2 with FP64 atomics
@@ -323,11 +493,151 @@ __global__ void __launch_bounds__(TileCfg<T, R>::NT, TileCfg<T, R>::MINB)
             const cplx *__restrict__ x, cplx *__restrict__ y, const double *__restrict__ diag)
 {
   extern __shared__ double2 tile[];
-  __shared__ double csign_small[SMALL ? SMALL_TERMS : 1];
+  __shared__ __align__(16) double csign_small[SMALL ? SMALL_TERMS : 2];
   // staged large passes keep their term tables in dynamic shared memory right behind the tile
   double *csign = SMALL ? csign_small : reinterpret_cast<double *>(tile + (1 << T));
   const i64 outer = tile_outer_bits(P, blockIdx.x);
   tile_body<T, R, SMALL>(P, S, outer, thread_base(P, outer), x, y, diag, tile, csign);
+}
+
+// ---- pipelined persistent kernel ----------------------------------------------------------
+// k_tiled serialises, inside a CTA, "fetch the tile -> arithmetic -> fetch old y -> store"; the
+// memory system only stays busy because other CTAs of the SM are in a different phase, and a
+// 128 KiB tile (T=13, the size that needs the fewest sweeps over HBM) leaves room for one CTA
+// only.  Here a persistent CTA walks tiles handed out by a ticket counter and keeps SEVEN
+// quarter-tile buffers (a quarter = the two rows 2q, 2q+1 of every thread): four hold the tile
+// being evaluated, the other three receive quarters 0..2 of the NEXT tile (cp.async) while the
+// arithmetic runs.  After the arithmetic the last quarter of the next tile goes into a buffer
+// the finished tile frees, together with the old y of the finished tile (read-modify-write
+// passes; six rows through the freed buffers, two through registers) -- one exposed round trip
+// per tile instead of two plus a whole tile fetch.
+template <int T>
+struct RingCfg {
+  static constexpr int R = 8;
+  static constexpr int NT = 1 << (T - 3);
+  static constexpr int LOG_NT = T - 3;
+  static constexpr int QUARTER = 1 << (T - 2);  // amplitudes per quarter tile
+  static constexpr int SLOTS = 7;
+  static constexpr size_t RING_BYTES = (size_t)SLOTS * QUARTER * sizeof(double2);
+  // resident CTAs per SM: 1024 threads of 64 registers, and 228 KiB of shared memory
+  static constexpr int BY_REGS = 65536 / (NT * 64) < 1 ? 1 : 65536 / (NT * 64);
+  static constexpr int BY_SMEM = (int)(233472 / (RING_BYTES + 2048));
+  static constexpr int CTAS = BY_REGS < BY_SMEM ? BY_REGS : BY_SMEM;
+};
+
+template <int T, bool SMALL>
+__global__ void __launch_bounds__(RingCfg<T>::NT, RingCfg<T>::CTAS)
+    k_tiled_ring(const __grid_constant__ PassParams P, const __grid_constant__ SmallTables S,
+                 const cplx *__restrict__ x, cplx *__restrict__ y, const double *__restrict__ diag,
+                 unsigned long long ntiles, unsigned long long *ticket)
+{
+  typedef RingCfg<T> C;
+  constexpr int NT = C::NT, LOG_NT = C::LOG_NT, R = C::R, Q = C::QUARTER;
+  extern __shared__ double2 ring[];
+  __shared__ __align__(16) double csign_small[SMALL ? SMALL_TERMS : 2];
+  __shared__ unsigned long long s_tile;
+  double *csign = SMALL ? csign_small : reinterpret_cast<double *>(ring + C::SLOTS * Q);
+  const int tid = threadIdx.x;
+  const i64 tbase = __ldg(&P.rowoff[tid >> P.B]) | (i64)(tid & ((1 << P.B) - 1));
+  const bool rmw = P.accumulate == 1;
+
+  // element offsets of the buffers: cur[q] holds quarter q of the tile being evaluated, nxt[q]
+  // receives quarter q (< 3) of the next one
+  int cur[4] = {0, Q, 2 * Q, 3 * Q};
+  int nxt[3] = {4 * Q, 5 * Q, 6 * Q};
+
+  if (tid == 0) s_tile = atomicAdd(ticket, 1ull);
+  __syncthreads();
+  unsigned long long tile_id = s_tile;
+  __syncthreads();  // s_tile is rewritten at the top of the loop
+  i64 outer = 0, base_g = 0;
+  double dg[R];  // the diagonal of the tile about to be evaluated (writing pass)
+  if (tile_id < ntiles) {
+    outer = tile_outer_bits(P, tile_id);
+    base_g = outer | tbase;
+#pragma unroll
+    for (int r = 0; r < R; ++r) cp_async16(&ring[cur[r >> 1] + (r & 1) * NT + tid], &x[base_g | P.roff[r]]);
+    if (diag != nullptr) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) dg[r] = __ldg(&diag[base_g | P.roff[r]]);
+    }
+  }
+  cp_async_commit();
+
+#pragma unroll 1
+  while (tile_id < ntiles) {
+    const i64 outer_g = outer | P.rank_bits;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1ull);  // the tile after this one
+    stage_tables<NT, SMALL>(P, S, outer_g, csign);
+    cp_async_wait<0>();
+    __syncthreads();  // the whole tile (and its scratch, and s_tile) is visible
+    const unsigned long long next_id = s_tile;
+    i64 outer_n = 0, base_n = 0;
+    if (next_id < ntiles) {
+      outer_n = tile_outer_bits(P, next_id);
+      base_n = outer_n | tbase;
+      if (!(P.debug & 2))
+#pragma unroll
+      for (int r = 0; r < 6; ++r) cp_async16(&ring[nxt[r >> 1] + (r & 1) * NT + tid], &x[base_n | P.roff[r]]);
+    }
+    cp_async_commit();
+
+    double ar[R], ai[R];
+    if (diag != nullptr) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const double2 v = ring[cur[r >> 1] + (r & 1) * NT + tid];
+        ar[r] = dg[r] * v.x;
+        ai[r] = dg[r] * v.y;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) ar[r] = ai[r] = 0.0;
+    }
+    if (!(P.debug & 1)) process_groups<R, LOG_NT, SMALL, true>(P, S, ring, csign, outer_g, ar, ai, cur);
+
+    __syncthreads();  // nobody reads this tile (or its scratch) any more
+    if (next_id < ntiles && !(P.debug & 2)) {
+#pragma unroll
+      for (int r = 6; r < R; ++r) cp_async16(&ring[cur[0] + (r & 1) * NT + tid], &x[base_n | P.roff[r]]);
+    }
+    if (rmw && !(P.debug & 4)) {
+      // old y: rows 0..5 through the three buffers this tile frees (each thread reads back only
+      // what it copied itself), rows 6 and 7 through registers
+#pragma unroll
+      for (int r = 0; r < 6; ++r) cp_async16(&ring[cur[1 + (r >> 1)] + (r & 1) * NT + tid], &y[base_g | P.roff[r]]);
+      const double2 o6 = y[base_g | P.roff[6]], o7 = y[base_g | P.roff[7]];
+      cp_async_commit();
+      cp_async_wait<0>();
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        const double2 old = ring[cur[1 + (r >> 1)] + (r & 1) * NT + tid];
+        y[base_g | P.roff[r]] = make_double2(ar[r] + old.x, ai[r] + old.y);
+      }
+      y[base_g | P.roff[6]] = make_double2(ar[6] + o6.x, ai[6] + o6.y);
+      y[base_g | P.roff[7]] = make_double2(ar[7] + o7.x, ai[7] + o7.y);
+    } else {
+      cp_async_commit();
+#pragma unroll
+      for (int r = 0; r < R; ++r) y[base_g | P.roff[r]] = make_double2(ar[r], ai[r]);
+    }
+    if (diag != nullptr && next_id < ntiles) {  // in flight together with the last quarter
+#pragma unroll
+      for (int r = 0; r < R; ++r) dg[r] = __ldg(&diag[base_n | P.roff[r]]);
+    }
+    // rotate the buffers
+    const int c0 = cur[0], c1 = cur[1], c2 = cur[2], c3 = cur[3];
+    cur[0] = nxt[0];
+    cur[1] = nxt[1];
+    cur[2] = nxt[2];
+    cur[3] = c0;
+    nxt[0] = c1;
+    nxt[1] = c2;
+    nxt[2] = c3;
+    tile_id = next_id;
+    outer = outer_n;
+    base_g = base_n;
+  }
 }
 
 // every pass of a small problem in ONE launch (blockIdx.y = pass): a pass of an L2-resident vector
@@ -379,7 +689,7 @@ __global__ void __launch_bounds__(TileCfg<T, R>::NT, TileCfg<T, R>::MINB)
                   const double *__restrict__ diag)
 {
   extern __shared__ double2 tile[];
-  __shared__ double csign[SMALL_TERMS];
+  __shared__ __align__(16) double csign[SMALL_TERMS];
   __shared__ unsigned long long s_item;
   const int tiles = 1 << F.log_tiles;
   const unsigned long long per_step = (unsigned long long)F.npasses * tiles;

@@ -189,7 +189,9 @@ int dnm_mat_size(dnm_mat_t A, int64_t *M, int64_t *N);
 /* MATOP_DESTROY  _backend/bcuda_template_2.cu:110-139 */
 int dnm_mat_destroy(dnm_mat_t A);
 /* Tuning / introspection knobs.  keys: "kernel" (0 auto, 1 general gather,
- * 2 tiled window), "tile_bits", "verbose". */
+ * 2 tiled window), "tile_bits" (0 auto, 8..13), "tile_rows" (0 auto, 8, 16),
+ * "pipeline" (0 auto, 1 pipelined persistent tiled kernel, 2 one tile per CTA),
+ * "verbose". */
 int dnm_mat_set_option(dnm_mat_t A, const char *key, int64_t value);
 /* keys: "kernel", "passes", "unique_masks", "nterms", "model_bytes",
  * "compulsory_bytes", "launches_per_mult" */
