@@ -613,6 +613,14 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
       for (int g = 0; g < ps.p.ngroups; ++g)
         ps.st.gd[g] = make_uint4(lam[g], sw[2 * g], sw[2 * g + 1],
                                  (rb[2 * g] & 0xffu) | ((rb[2 * g + 1] & 0xffu) << 8) | ((u32)(kp[g] & 1) << 16));
+    if (lean && getenv("DNM_NO_CPLX") == nullptr)
+      for (int g = 0; g + 1 < ps.p.ngroups; ++g) {
+        const bool plain_pair = (ps.st.gd[g].w & 0xffffu) == 0 && (ps.st.gd[g + 1].w & 0xffffu) == 0;
+        if (lam[g] == lam[g + 1] && !(kp[g] & 1) && (kp[g + 1] & 1) && plain_pair) {
+          ps.st.gd[g].x |= 0x80000000u;
+          ++g;
+        }
+      }
     ps.p.lean = lean ? 1 : 0;
     if (const char *e = getenv("DNM_RING_DEBUG")) ps.p.debug = atoi(e);
   }

@@ -90,6 +90,8 @@ struct SmallTables {
   u8 role[SMALL_TERMS];  // 0: ordinary term, 1 / 2: first / second entry of a PATH_PAIR group
   // lean passes: one 16-byte descriptor per group
   //   x = lam, y = window bits of s1, z = window bits of s1^s2, w = pat(s1) | pat(s1^s2) << 8 | imag << 16
+  // x bit 31: the next group is the imaginary group of the same mask and neither has a row
+  // pattern -- the two share one gather (X and Y fields, hopping with complex amplitudes)
   uint4 gd[SMALL_GROUPS];
 };
 
@@ -138,6 +140,37 @@ __device__ __forceinline__ void cp_async_wait()
 // HI is a template parameter, so in a contiguous tile every LDS has an immediate offset and there
 // is no per-row address arithmetic.  RING (ring kernel): rows live in pairs (quarters of the
 // tile) at element offsets qoff[0..R/2) of the ring buffer.
+// one gather serving a real and an imaginary group of the same mask: acc += (cr + i*ci) * x
+template <int R, int LOG_NT, int HI, bool RING>
+__device__ __forceinline__ void gather_fixed_cplx(double (&ar)[R], double (&ai)[R], const double2 *col, const int *qoff,
+                                                  double cr, double ci)
+{
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const double2 v = RING ? col[qoff[(r ^ HI) >> 1] + (((r ^ HI) & 1) << LOG_NT)] : col[(r ^ HI) << LOG_NT];
+    ar[r] += cr * v.x;
+    ar[r] -= ci * v.y;
+    ai[r] += cr * v.y;
+    ai[r] += ci * v.x;
+  }
+}
+
+template <int R, int LOG_NT, bool RING>
+__device__ __forceinline__ void gather_switch_cplx(double (&ar)[R], double (&ai)[R], const double2 *col,
+                                                   const int *qoff, int hi_l, double cr, double ci)
+{
+#define DNM_HI_CASE(H) \
+  case H:               \
+    if (H < R) gather_fixed_cplx<R, LOG_NT, (H < R ? H : 0), RING>(ar, ai, col, qoff, cr, ci); \
+    break;
+  switch (hi_l) {
+    DNM_HI_CASE(0) DNM_HI_CASE(1) DNM_HI_CASE(2) DNM_HI_CASE(3) DNM_HI_CASE(4) DNM_HI_CASE(5) DNM_HI_CASE(6)
+    DNM_HI_CASE(7)
+    default: break;
+  }
+#undef DNM_HI_CASE
+}
+
 template <int R, int LOG_NT, int HI, bool IMAG, bool SCALAR, bool RING>
 __device__ __forceinline__ void gather_fixed(double (&ar)[R], double (&ai)[R], const double2 *col, const int *qoff,
                                              double d0, const double (&d)[R])
@@ -266,11 +299,21 @@ __device__ __forceinline__ void process_groups_lean(const PassParams &P, const S
     const uint4 gd = S.gd[g];
     const double2 cc = cpm[g];
     const double2 *col = tile + (tid ^ (int)(gd.x & (NT - 1)));
-    const int hi = (int)(gd.x >> LOG_NT);
+    const int hi = (int)((gd.x & 0x7fffffffu) >> LOG_NT);
     const int pa = __popc(gd.y & (u32)tid) & 1, pb = __popc(gd.z & (u32)tid) & 1;
     const bool imag = (gd.w >> 16) != 0;
     if ((gd.w & 0xffffu) == 0) {
       const double c = flip_sign(pb ? cc.y : cc.x, pa);
+      if (gd.x >> 31) {
+        // real and imaginary group of one mask: one fetch, a complex coefficient
+        ++g;
+        const uint4 gi = S.gd[g];
+        const double2 ci2 = cpm[g];
+        const int qa = __popc(gi.y & (u32)tid) & 1, qb = __popc(gi.z & (u32)tid) & 1;
+        const double ci = flip_sign(qb ? ci2.y : ci2.x, qa);
+        if (c != 0.0 || ci != 0.0) gather_switch_cplx<R, LOG_NT, RING>(ar, ai, col, qoff, hi, c, ci);
+        continue;
+      }
       if (c != 0.0) {
         const double none[R] = {};
         if (imag) gather_switch<R, LOG_NT, true, true, RING>(ar, ai, col, qoff, hi, c, none);

@@ -9,7 +9,7 @@ from dynamite_b200._backend import bpetsc
 _capi.ensure_gpu(0)
 lib = _capi.lib()
 L = int(sys.argv[1])
-H = build_hamiltonian('MBL', L); H.reduce_msc()
+H = build_hamiltonian(os.environ.get('DNM_MODEL', 'MBL'), L); H.reduce_msc()
 sub = Full(L=L)
 masks, offs = msc_tools.mask_offsets(H.msc)
 n = 1 << L
