@@ -215,6 +215,13 @@ struct TiledPlan {
   cplx *stage[2] = {nullptr, nullptr};
   cudaEvent_t ev_staged[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   double cost = 0.0;  // estimated HBM sweeps per MatMult
+  // which part of a partner's shard this rank reads at all (DMA staging copies only that):
+  // kind 0 = everything, 1 = nothing (the group's passes are skipped too), 2 = [first, first+count)
+  struct Need {
+    int kind = 0;
+    i64 first = 0, count = 0;
+  };
+  std::map<int, Need> need;
   ~TiledPlan()
   {
     for (auto &ps : passes)
@@ -988,6 +995,62 @@ void build_units(TiledPlan &plan, int verbose)
   }
 }
 
+// Which amplitudes of the partner's shard a remote group can touch on THIS rank.  A group whose
+// terms come in pairs of equal magnitude (XX+YY: c1 = +-c2) has D(I) = sigma(s1.I) c1 (1 + eps sigma(sB.I)),
+// zero on the half space parity(sB & I) != e; when sB only involves rank bits the whole group is
+// either needed or not, when its only local bit is the top one the needed half is contiguous.
+TiledPlan::Need stage_need(const std::vector<const NMask *> &masks, int nloc)
+{
+  TiledPlan::Need all;
+  const i64 lmask = ((i64)1 << nloc) - 1;
+  const i64 top = (i64)1 << (nloc - 1);
+  const i64 rank_bits = (i64)G.rank << nloc;
+  bool have = false, none = true;
+  int half = -1;
+  for (const NMask *nm : masks) {
+    for (int kind = 0; kind < 2; ++kind) {
+      std::vector<std::pair<i64, double>> uniq;
+      for (const NTerm &t : nm->terms) {
+        if ((int)t.imag != kind) continue;
+        bool found = false;
+        for (auto &u : uniq)
+          if (u.first == t.sign) {
+            u.second += t.coef;
+            found = true;
+          }
+        if (!found) uniq.emplace_back(t.sign, t.coef);
+      }
+      if (uniq.empty()) continue;
+      have = true;
+      if (uniq.size() != 2 || std::fabs(uniq[0].second) != std::fabs(uniq[1].second) || uniq[0].second == 0.0) return all;
+      const i64 sb = uniq[0].first ^ uniq[1].first;
+      const int e = (uniq[0].second == uniq[1].second) ? 0 : 1;  // rows with parity(sb & I) == e survive
+      const int v = e ^ parity64(sb & rank_bits);                // ... i.e. parity(sb & i) == v on this rank
+      const i64 sl = sb & lmask;
+      if (sl == 0) {
+        if (v == 0) return all;  // every local row survives
+        continue;                // no local row survives: this (mask, kind) needs nothing
+      }
+      if (sl != top) return all;
+      // rows with top bit == v read partner amplitudes with top bit == v ^ (mask's top bit)
+      const int h = v ^ (int)(((nm->mask & lmask) >> (nloc - 1)) & 1);
+      if (half >= 0 && half != h) return all;
+      half = h;
+      none = false;
+    }
+  }
+  if (!have) return all;
+  TiledPlan::Need nd;
+  if (none) {
+    nd.kind = 1;
+  } else {
+    nd.kind = 2;
+    nd.first = half ? top : 0;
+    nd.count = top;
+  }
+  return nd;
+}
+
 // One candidate plan for a fixed tile size T and run length 2^B.
 std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &masks, int T, int R, int B, int verbose)
 {
@@ -1040,9 +1103,19 @@ std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &mas
         plan_group(*plan, kv.second, kv.first, T, R, B, first_local, verbose);
         first_local = false;
       } else {
+        const size_t before = plan->passes.size(), dbefore = plan->directs.size();
         plan_group(*plan, kv.second, kv.first, T, R, B, plan->overlap && first_remote, verbose);
         first_remote = false;
         plan->any_remote = true;
+        // partial staging is only safe where a zero coefficient never touches the operand (lean passes)
+        bool lean_only = plan->directs.size() == dbefore;
+        for (size_t k = before; k < plan->passes.size(); ++k) lean_only = lean_only && plan->passes[k].small && plan->passes[k].p.lean;
+        if (plan->dma && lean_only && getenv("DNM_FULL_STAGE") == nullptr) {
+          plan->need[kv.first] = stage_need(kv.second, nloc);
+          if (verbose)
+            fprintf(stderr, "[dnm] rank %d partner^%d: staging kind %d first %lld count %lld\n", G.rank, kv.first,
+                    plan->need[kv.first].kind, (long long)plan->need[kv.first].first, (long long)plan->need[kv.first].count);
+        }
       }
     }
   }
@@ -1208,11 +1281,25 @@ void tiled_mult(dnm_mat_s *A, dnm_vec_t xv, dnm_vec_t yv)
       first = false;
       ++launches;
     }
-    // ... while the copy engines stage the partner shards, two buffers deep
+    // ... while the copy engines stage the partner shards, two buffers deep.  Only the part of a
+    // shard this rank can touch travels (plan.need): all of it, a contiguous half, or nothing.
+    size_t used = 0;
     for (size_t gi = 0; gi < partners.size(); ++gi) {
-      const int b = (int)(gi % nbuf);
-      if ((int)gi >= nbuf) DNM_CHECK_CUDA(cudaStreamWaitEvent(G.stream2, plan.ev_free[b], 0));
-      DNM_CHECK_CUDA(cudaMemcpyAsync(plan.stage[b], source(partners[gi]), bytes, cudaMemcpyDeviceToDevice, G.stream2));
+      TiledPlan::Need nd;
+      auto it = plan.need.find(partners[gi]);
+      if (it != plan.need.end()) nd = it->second;
+      if (nd.kind == 1) continue;  // every coefficient of this group vanishes on this rank
+      const int b = (int)(used % nbuf);
+      if ((int)used >= nbuf) DNM_CHECK_CUDA(cudaStreamWaitEvent(G.stream2, plan.ev_free[b], 0));
+      ++used;
+      const cplx *src = source(partners[gi]);
+      if (nd.kind == 2 && getenv("DNM_POISON_STAGE"))  // tests: the part that does not travel must never be used
+        DNM_CHECK_CUDA(cudaMemsetAsync(plan.stage[b], 0xff, bytes, G.stream2));
+      if (nd.kind == 2)
+        DNM_CHECK_CUDA(cudaMemcpyAsync(plan.stage[b] + nd.first, src + nd.first, sizeof(cplx) * (size_t)nd.count,
+                                       cudaMemcpyDeviceToDevice, G.stream2));
+      else
+        DNM_CHECK_CUDA(cudaMemcpyAsync(plan.stage[b], src, bytes, cudaMemcpyDeviceToDevice, G.stream2));
       DNM_CHECK_CUDA(cudaEventRecord(plan.ev_staged[b], G.stream2));
       // the group's passes read the staged copy as ordinary local memory
       DNM_CHECK_CUDA(cudaStreamWaitEvent(G.stream, plan.ev_staged[b], 0));

@@ -70,6 +70,17 @@ def main():
                 H.get_mat().set_option('tile_bits', 0)      # drops the cached plan
                 y2 = H.dot(x)
                 check(f'matmult[{mode}] {name} L={L}', rel_err(y2.vec[a:b], want[a:b]) < 1e-12)
+            # DMA staging copies only the part of a partner shard this rank can touch (XX+YY terms:
+            # half of it or nothing); the rest of the staging buffer is poisoned with NaNs here
+            os.environ['DNM_POISON_STAGE'] = '1'
+            y3 = H.dot(x)
+            check(f'matmult[dma, poisoned staging] {name} L={L}', rel_err(y3.vec[a:b], want[a:b]) < 1e-12)
+            os.environ['DNM_FULL_STAGE'] = '1'
+            H.get_mat().set_option('tile_bits', 0)
+            y4 = H.dot(x)
+            check(f'matmult[dma, full staging] {name} L={L}', rel_err(y4.vec[a:b], want[a:b]) < 1e-12)
+            os.environ.pop('DNM_POISON_STAGE', None)
+            os.environ.pop('DNM_FULL_STAGE', None)
             os.environ.pop('DNM_REMOTE', None)
             H.get_mat().set_option('tile_bits', 0)
             nrm = H.infinity_norm()
