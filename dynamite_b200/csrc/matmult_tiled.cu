@@ -411,8 +411,90 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
   const bool small_pass = general_groups <= (size_t)SMALL_GROUPS && general_terms + general_groups <= (size_t)SMALL_TERMS &&
                           getenv("DNM_NO_PAIR") == nullptr;
   bool any_table = false;
+  // GF(2) basis (at most 6 vectors) of the sign masks of `all`; coords[t] = which basis vectors XOR
+  // to term t's mask
+  auto gf2_basis = [&](const std::vector<const NTerm *> &all, std::vector<i64> &basis, std::vector<u32> &coords) -> bool {
+    std::vector<i64> reduced;     // eliminated forms of the basis vectors
+    std::vector<u32> red_coord;   // their coordinates in `basis`
+    coords.assign(all.size(), 0);
+    for (size_t ti = 0; ti < all.size(); ++ti) {
+      i64 v = all[ti]->sign;
+      u32 c = 0;
+      for (bool changed = true; changed;) {  // reduced[] is not kept in echelon order: iterate to a fixed point
+        changed = false;
+        for (size_t k = 0; k < reduced.size(); ++k) {
+          const i64 top = (i64)1 << (63 - __builtin_clzll((unsigned long long)reduced[k]));
+          if (v & top) {
+            v ^= reduced[k];
+            c ^= red_coord[k];
+            changed = true;
+          }
+        }
+      }
+      if (v != 0) {
+        if (basis.size() >= 6) return false;
+        // new independent vector: the term's own mask joins the basis
+        const u32 self = 1u << basis.size();
+        basis.push_back(all[ti]->sign);
+        reduced.push_back(v);
+        red_coord.push_back(c ^ self);
+        c = self;
+      }
+      coords[ti] = c;
+    }
+    return true;
+  };
+  // append the basis vectors as the group's "terms"; returns the per-row index bits (byte r = row group r)
+  auto push_basis = [&](const std::vector<i64> &basis) -> unsigned long long {
+    unsigned long long rp = 0;
+    for (size_t k = 0; k < basis.size(); ++k) {
+      const u32 w = extract(basis[k] & lmask);
+      const u32 bits = row_pattern(w);
+      sw.push_back(w);
+      rb.push_back(bits);
+      so.push_back(basis[k] & ~wbits);
+      cf.push_back(0.0);
+      for (int r = 0; r < R; ++r)
+        if ((bits >> r) & 1u) rp |= (unsigned long long)1 << (8 * r + (int)k);
+    }
+    return rp;
+  };
   for (const NMask *nm : masks) {
     const u32 l = extract(nm->mask & lmask);
+    if (allow_tables && getenv("DNM_NO_CTABLE") == nullptr) {
+      // masks with real AND imaginary terms: one joint basis, one table of complex coefficients,
+      // one gather (SYK: 8 + 8 terms per mask, joint dimension 5)
+      std::vector<const NTerm *> all;
+      size_t nre = 0;
+      for (const NTerm &t : nm->terms)
+        if (!t.imag) all.push_back(&t);
+      nre = all.size();
+      for (const NTerm &t : nm->terms)
+        if (t.imag) all.push_back(&t);
+      std::vector<i64> basis;
+      std::vector<u32> coords;
+      if (nre > 0 && nre < all.size() && all.size() >= 4 && gf2_basis(all, basis, coords)) {
+        const int d = (int)basis.size();
+        lam.push_back(l);
+        if (tabs.size() & 1) tabs.push_back(0.0);  // complex entries are read as 16-byte words
+        toff.push_back((u32)tabs.size());
+        t0.push_back((u16)sw.size());
+        for (u32 p = 0; p < (1u << d); ++p) {
+          double re = 0.0, im = 0.0;
+          for (size_t ti = 0; ti < all.size(); ++ti)
+            (ti < nre ? re : im) += (__builtin_parity(coords[ti] & p) ? -1.0 : 1.0) * all[ti]->coef;
+          tabs.push_back(re);
+          tabs.push_back(im);
+        }
+        rpat.push_back(push_basis(basis));
+        t1.push_back((u16)sw.size());
+        t2.push_back((u16)sw.size());
+        pat.push_back(0);
+        kp.push_back((u8)(PATH_CTABLE << 1));
+        any_table = true;
+        continue;
+      }
+    }
     for (int kind = 0; kind < 2; ++kind) {
       std::vector<const NTerm *> plain, rowdep;
       for (const NTerm &t : nm->terms) {
@@ -468,42 +550,11 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
       }
       t0.push_back((u16)sw.size());
       if (allow_tables && plain.size() + rowdep.size() >= 4) {
-        // GF(2) basis of the sign masks; coords[t] = which basis vectors XOR to term t's mask
         std::vector<const NTerm *> all(plain);
         all.insert(all.end(), rowdep.begin(), rowdep.end());
-        std::vector<i64> basis, reduced;       // original-form basis vectors and their eliminated forms
-        std::vector<u32> red_coord;            // coordinates (in `basis`) of each eliminated form
-        std::vector<u32> coords(all.size(), 0);
-        bool ok = true;
-        for (size_t ti = 0; ti < all.size() && ok; ++ti) {
-          i64 v = all[ti]->sign;
-          u32 c = 0;
-          for (bool changed = true; changed;) {  // reduced[] is not kept in echelon order: iterate to a fixed point
-            changed = false;
-            for (size_t k = 0; k < reduced.size(); ++k) {
-              const i64 top = (i64)1 << (63 - __builtin_clzll((unsigned long long)reduced[k]));
-              if (v & top) {
-                v ^= reduced[k];
-                c ^= red_coord[k];
-                changed = true;
-              }
-            }
-          }
-          if (v != 0) {
-            if (basis.size() >= 6) {
-              ok = false;
-              break;
-            }
-            // new independent vector: the term's own mask joins the basis
-            const u32 self = 1u << basis.size();
-            basis.push_back(all[ti]->sign);
-            reduced.push_back(v);
-            red_coord.push_back(c ^ self);
-            c = self;
-          }
-          coords[ti] = c;
-        }
-        if (ok) {
+        std::vector<i64> basis;
+        std::vector<u32> coords;
+        if (gf2_basis(all, basis, coords)) {
           const int d = (int)basis.size();
           toff.back() = (u32)tabs.size();
           for (u32 p = 0; p < (1u << d); ++p) {
@@ -511,18 +562,7 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
             for (size_t ti = 0; ti < all.size(); ++ti) acc += (__builtin_parity(coords[ti] & p) ? -1.0 : 1.0) * all[ti]->coef;
             tabs.push_back(acc);
           }
-          unsigned long long rp = 0;
-          for (int k = 0; k < d; ++k) {
-            const u32 w = extract(basis[k] & lmask);
-            const u32 bits = row_pattern(w);
-            sw.push_back(w);
-            rb.push_back(bits);
-            so.push_back(basis[k] & ~wbits);
-            cf.push_back(0.0);
-            for (int r = 0; r < R; ++r)
-              if ((bits >> r) & 1u) rp |= (unsigned long long)1 << (8 * r + k);
-          }
-          rpat.back() = rp;
+          rpat.back() = push_basis(basis);
           t1.push_back((u16)sw.size());
           t2.push_back((u16)sw.size());
           pat.push_back(0);

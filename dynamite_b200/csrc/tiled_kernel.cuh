@@ -30,7 +30,7 @@ constexpr int SMALL_TERMS = 96;   // (constant) memory; bigger ones read them fr
 
 constexpr int MAX_SEGS = 12;
 
-enum { PATH_SCALAR = 0, PATH_TWO = 1, PATH_GENERAL = 2, PATH_TABLE = 3, PATH_PAIR = 4 };
+enum { PATH_SCALAR = 0, PATH_TWO = 1, PATH_GENERAL = 2, PATH_TABLE = 3, PATH_PAIR = 4, PATH_CTABLE = 5 };
 
 struct PassParams {
   int ngroups;
@@ -55,6 +55,8 @@ struct PassParams {
   // PATH_TABLE groups (many terms per mask): the terms' sign masks span a GF(2) space of dimension
   // d <= 6; the group's "terms" t0..t1 are the d basis vectors and the coefficient of a row is
   // tabs[toff + index], index bit k = parity(basis_k & row)
+  // PATH_CTABLE: the same for a mask with real and imaginary terms -- joint basis, table entries
+  // are complex (re, im) pairs at the even offset toff, one gather serves both parts
   const double *tabs;
   const u32 *toff;                 // [ngroups]
   const unsigned long long *rpat;  // [ngroups] byte r = index bits contributed by row group r
@@ -162,6 +164,39 @@ __device__ __forceinline__ void gather_switch_cplx(double (&ar)[R], double (&ai)
 #define DNM_HI_CASE(H) \
   case H:               \
     if (H < R) gather_fixed_cplx<R, LOG_NT, (H < R ? H : 0), RING>(ar, ai, col, qoff, cr, ci); \
+    break;
+  switch (hi_l) {
+    DNM_HI_CASE(0) DNM_HI_CASE(1) DNM_HI_CASE(2) DNM_HI_CASE(3) DNM_HI_CASE(4) DNM_HI_CASE(5) DNM_HI_CASE(6)
+    DNM_HI_CASE(7)
+    default: break;
+  }
+#undef DNM_HI_CASE
+}
+
+// acc[r] += tab[q ^ rowbits(r)] * x(row r ^ HI): per-row complex coefficients read from a table
+template <int R, int LOG_NT, int HI, bool RING>
+__device__ __forceinline__ void gather_fixed_ctab(double (&ar)[R], double (&ai)[R], const double2 *col, const int *qoff,
+                                                  const double2 *tab, u32 q, unsigned long long rp)
+{
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const double2 c = __ldg(&tab[q ^ (u32)((rp >> (8 * (r & 7))) & 0xffull)]);
+    const double2 v = RING ? col[qoff[(r ^ HI) >> 1] + (((r ^ HI) & 1) << LOG_NT)] : col[(r ^ HI) << LOG_NT];
+    ar[r] += c.x * v.x;
+    ar[r] -= c.y * v.y;
+    ai[r] += c.x * v.y;
+    ai[r] += c.y * v.x;
+  }
+}
+
+template <int R, int LOG_NT, bool RING>
+__device__ __forceinline__ void gather_switch_ctab(double (&ar)[R], double (&ai)[R], const double2 *col,
+                                                   const int *qoff, int hi_l, const double2 *tab, u32 q,
+                                                   unsigned long long rp)
+{
+#define DNM_HI_CASE(H) \
+  case H:               \
+    if (H < R) gather_fixed_ctab<R, LOG_NT, (H < R ? H : 0), RING>(ar, ai, col, qoff, tab, q, rp); \
     break;
   switch (hi_l) {
     DNM_HI_CASE(0) DNM_HI_CASE(1) DNM_HI_CASE(2) DNM_HI_CASE(3) DNM_HI_CASE(4) DNM_HI_CASE(5) DNM_HI_CASE(6)
@@ -416,6 +451,19 @@ __device__ __forceinline__ void process_groups(const PassParams &P, const SmallT
 
     const int t1 = SMALL ? (int)S.t1[g] : (int)__ldg(&P.t1[g]);
     const int t2 = SMALL ? (int)S.t2[g] : (int)__ldg(&P.t2[g]);
+    if constexpr (!SMALL && R <= 8) if (path == PATH_CTABLE) {
+      // index of this thread into the group's table of complex coefficients: one parity per basis vector
+      u32 q = 0;
+      for (int t = t0; t < t1; ++t) {
+        u32 p;
+        if (P.staged) p = (u32)(__double2hiint(csign[t]) >> 31) ^ (u32)__popc(swrb[t].x & (u32)tid);
+        else p = (u32)__popcll((unsigned long long)(__ldg(&P.so[t]) & outer_g)) ^ (u32)__popc(__ldg(&P.sw[t]) & (u32)tid);
+        q |= (p & 1u) << (t - t0);
+      }
+      const double2 *tab = reinterpret_cast<const double2 *>(P.tabs + __ldg(&P.toff[g]));
+      gather_switch_ctab<R, LOG_NT, RING>(ar, ai, col, qoff, hi_lo, tab, q, __ldg(&P.rpat[g]));
+      continue;
+    }
     double c0 = 0.0;  // terms without r bits: one scalar per thread
     if (SMALL || path != PATH_TABLE)
       for (int t = t0; t < t1; ++t) c0 += term(t);
