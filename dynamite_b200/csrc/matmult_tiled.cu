@@ -210,6 +210,7 @@ struct TiledPlan {
   bool overlap = false;      // (peer-load mode) remote passes accumulate into y_remote on the side stream
   cplx *y_remote = nullptr;  // [local rows], allocated on first use
   PassParams *d_batch = nullptr;  // all passes' parameters, when the whole product runs as one batched launch
+  size_t batch_stage_bytes = 0;   // shared memory for the largest staged term table among them
   int batch_T = 0, batch_R = 0;
   bool dma = false;          // remote shards are staged by the copy engines while the local passes run
   cplx *stage[2] = {nullptr, nullptr};
@@ -392,6 +393,7 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
   std::vector<u32> lam, sw, rb, toff;
   std::vector<u16> t0, t1, t2, pat;
   std::vector<u8> kp, role;
+  std::vector<u16> cls;  // [ngroups * 8]: PATH_WHT groups, end of each row class inside t1..t2
   std::vector<i64> so;
   std::vector<double> cf, tabs;
   std::vector<unsigned long long> rpat;
@@ -578,6 +580,14 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
         cf.push_back(t->coef);
       }
       t1.push_back((u16)sw.size());
+      // many row-dependent terms (SYK two-flip masks: ~36 per group, GF(2) rank > 6): order them by
+      // row class rho = their sign bits on the row positions; the kernel sums each class into one
+      // per-thread scalar and a size-R Walsh-Hadamard transform turns those into the row coefficients
+      const bool use_wht = !small_pass && R == 8 && rowdep.size() >= 6 && getenv("DNM_NO_WHT") == nullptr;
+      if (use_wht)
+        std::stable_sort(rowdep.begin(), rowdep.end(), [&](const NTerm *a, const NTerm *b) {
+          return (extract(a->sign & lmask) >> log_nt) < (extract(b->sign & lmask) >> log_nt);
+        });
       bool one_pattern = true;
       u32 first_pat = 0;
       for (size_t k = 0; k < rowdep.size(); ++k) {
@@ -591,7 +601,16 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
         cf.push_back(rowdep[k]->coef);
       }
       t2.push_back((u16)sw.size());
-      const int path = rowdep.empty() ? PATH_SCALAR : (one_pattern ? PATH_TWO : PATH_GENERAL);
+      if (use_wht && !one_pattern) {
+        cls.resize(lam.size() * 8, 0);
+        u16 *c = &cls[(lam.size() - 1) * 8];
+        size_t k = 0;
+        for (int rho = 0; rho < 8; ++rho) {
+          while (k < rowdep.size() && (int)(extract(rowdep[k]->sign & lmask) >> log_nt) <= rho) ++k;
+          c[rho] = (u16)(t1.back() + k);
+        }
+      }
+      const int path = rowdep.empty() ? PATH_SCALAR : (one_pattern ? PATH_TWO : (use_wht ? PATH_WHT : PATH_GENERAL));
       pat.push_back((u16)first_pat);
       kp.push_back((u8)(kind | (path << 1)));
     }
@@ -620,6 +639,8 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
   ps.p.t2 = up(t2, ps.owned);
   ps.p.pat = up(pat, ps.owned);
   ps.p.kp = up(kp, ps.owned);
+  cls.resize(lam.size() * 8, 0);
+  ps.p.cls = up(cls, ps.owned);
   ps.p.tabs = up(tabs, ps.owned);
   ps.p.toff = up(toff, ps.owned);
   ps.p.rpat = up(rpat, ps.owned);
@@ -931,10 +952,17 @@ template <int T, int R>
 void launch_batch_tr(const TiledPlan &plan, const cplx *x, cplx *y, const double *diag)
 {
   static bool attr_set = false;
-  const size_t smem = sizeof(double2) << T;
+  const size_t smem = (sizeof(double2) << T) + plan.batch_stage_bytes;
   if (!attr_set) {
-    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_batch<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_batch<T, R>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_batch<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)((sizeof(double2) << T) + 40 * 1024)));
+    // table-driven passes read their coefficient tables through the L1: leave it what the CTAs
+    // of one SM (1024 threads) do not need as shared memory
+    const int ctas = std::max(1, 1024 / TileCfg<T, R>::NT);
+    int pct = (int)((ctas * (smem + 2048) * 100 + 233471) / 233472);
+    if (const char *e = getenv("DNM_BATCH_CARVEOUT")) pct = atoi(e);
+    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_batch<T, R>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        std::min(100, std::max(pct, 1))));
     attr_set = true;
   }
   const dim3 grid((unsigned)((long long)1 << (plan.nloc - T)), (unsigned)plan.passes.size());
@@ -1221,7 +1249,8 @@ TiledPlan *build_plan(dnm_mat_s *A)
       for (const Pass &ps : best->passes) {
         PassParams q = ps.p;
         q.accumulate = 2;
-        q.staged = 0;
+        if (getenv("DNM_NO_BATCH_STAGE")) q.staged = 0;
+        if (q.staged) best->batch_stage_bytes = std::max(best->batch_stage_bytes, (size_t)ps.nterms * 16);
         all.push_back(q);
       }
       DNM_CHECK_CUDA(cudaMalloc(&best->d_batch, sizeof(PassParams) * all.size()));

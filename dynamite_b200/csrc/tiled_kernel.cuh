@@ -30,7 +30,7 @@ constexpr int SMALL_TERMS = 96;   // (constant) memory; bigger ones read them fr
 
 constexpr int MAX_SEGS = 12;
 
-enum { PATH_SCALAR = 0, PATH_TWO = 1, PATH_GENERAL = 2, PATH_TABLE = 3, PATH_PAIR = 4, PATH_CTABLE = 5 };
+enum { PATH_SCALAR = 0, PATH_TWO = 1, PATH_GENERAL = 2, PATH_TABLE = 3, PATH_PAIR = 4, PATH_CTABLE = 5, PATH_WHT = 6 };
 
 struct PassParams {
   int ngroups;
@@ -58,6 +58,7 @@ struct PassParams {
   // PATH_CTABLE: the same for a mask with real and imaginary terms -- joint basis, table entries
   // are complex (re, im) pairs at the even offset toff, one gather serves both parts
   const double *tabs;
+  const u16 *cls;                  // [ngroups * 8] PATH_WHT: end of row class rho among the terms t1..t2
   const u32 *toff;                 // [ngroups]
   const unsigned long long *rpat;  // [ngroups] byte r = index bits contributed by row group r
   // term tables [nterms]
@@ -485,6 +486,34 @@ __device__ __forceinline__ void process_groups(const PassParams &P, const SmallT
 #pragma unroll
         for (int r = 0; r < RH; ++r) d[r] = ((pat >> r) & 1u) ? dm : dp;
         any = (dp != 0.0) || (dm != 0.0);
+      } else if (!SMALL && R == 8 && path == PATH_WHT) {
+        // E[rho] = sum of the class-rho terms (per-thread scalars); d[r] = sum_rho (-1)^popc(rho & r) E[rho]
+        double E[8];
+        int t = t1;
+#pragma unroll
+        for (int rho = 0; rho < 8; ++rho) {
+          const int te = (int)__ldg(&P.cls[g * 8 + rho]);
+          double e = (rho == 0) ? c0 : 0.0;
+          for (; t < te; ++t) e += term(t);
+          E[rho] = e;
+        }
+#pragma unroll
+        for (int h = 1; h < 8; h <<= 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (!(i & h)) {
+              const double a = E[i], b = E[i | h];
+              E[i] = a + b;
+              E[i | h] = a - b;
+            }
+          }
+        }
+        any = false;
+#pragma unroll
+        for (int r = 0; r < RH; ++r) {
+          d[r] = E[r & 7];
+          any = any || (d[r] != 0.0);
+        }
       } else if (!SMALL && path == PATH_TABLE) {
         // index of this thread's rows into the group's coefficient table: one parity per basis vector
         u32 q = 0;
