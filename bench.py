@@ -204,7 +204,7 @@ def run_reference(args, rank, world):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def time_region(lib, fn, steps, dist):
@@ -443,13 +443,34 @@ def run_ours(args, rank, world, local_rank):
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
             'extras': extras,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
 mat_info_cache = {}
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """Keep the process's stdout for the ONE result line: everything else any library prints there
+    (NCCL's version banner under NCCL_DEBUG=VERSION/WARN, for one) is sent to stderr."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(out):
+    line = (json.dumps(out) + '\n').encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_RESULT_FD, line)
 
 
 def main():
@@ -458,6 +479,8 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ['WORLD_SIZE']) if under_torchrun else 1
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if under_torchrun or args.gpus <= 1:
+        claim_stdout()  # (the re-launching parent below must pass its children's stdout through)
     if args.impl == 'reference':
         # rank 0 alone runs the CPU arm; it describes the N-GPU workload (L = 30 + log2 N)
         run_reference(args, rank, max(world, args.gpus))
