@@ -13,8 +13,9 @@ def test_reference_arm_prints_contract_line():
                           '--steps', '2', '--warmup', '1', '--cpu-seconds', '0.2'],
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stderr[-2000:]
-    line = [ln for ln in res.stdout.splitlines() if ln.startswith('{')][-1]
-    out = json.loads(line)
+    # stdout carries exactly the result line: anything a library prints there goes to stderr
+    assert len(res.stdout.splitlines()) == 1, res.stdout[:500]
+    out = json.loads(res.stdout)
     assert out['impl'] == 'reference' and out['metric'] == 'shell_matmult_per_s'
     assert out['higher_is_better'] is True and out['scaling'] == 'weak' and out['vs_baseline'] is None
     assert out['value'] > 0 and out['steps'] == 2 and out['warmup'] == 1
