@@ -625,6 +625,23 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
     rowoff[h] = off;
   }
   role.resize(sw.size(), 0);
+  // the same offsets as runs of consecutive window positions (opt-in arithmetic deposit in thread_base)
+  ps.p.n_rseg = 0;
+  if (getenv("DNM_ROWOFF_ARITH")) {
+    int b = B;
+    while (b < T) {
+      int e = b + 1;
+      while (e < T && W[e] == W[e - 1] + 1) ++e;
+      if (ps.p.n_rseg == MAX_SEGS) {
+        ps.p.n_rseg = 0;  // too many runs: keep the table
+        break;
+      }
+      ps.p.rseg_mask[ps.p.n_rseg] = ((1u << (e - b)) - 1u) << (b - B);
+      ps.p.rseg_shift[ps.p.n_rseg] = (unsigned char)(W[b] - (b - B));
+      ++ps.p.n_rseg;
+      b = e;
+    }
+  }
   ps.p.ngroups = (int)lam.size();
   ps.p.nterms = (int)sw.size();
   ps.p.B = B;

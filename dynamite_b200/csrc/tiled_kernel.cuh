@@ -78,6 +78,11 @@ struct PassParams {
   // every group is a PATH_PAIR group at t0 = 2g with row patterns of at most 8 bits: the kernels
   // run the lean group loop on SmallTables::gd
   int lean;
+  // opt-in (DNM_ROWOFF_ARITH, untuned): rowoff[h] deposited arithmetically from runs of consecutive
+  // window positions, like the tile number, instead of the dependent global load (n_rseg > 0)
+  int n_rseg;
+  unsigned char rseg_shift[MAX_SEGS];
+  unsigned int rseg_mask[MAX_SEGS];
   int debug;  // timing experiments only (DNM_RING_DEBUG): bit 0 skip the arithmetic, bit 1 skip the x fetches, bit 2 skip old y
 };
 
@@ -262,6 +267,12 @@ __device__ __forceinline__ i64 tile_outer_bits(const PassParams &P, unsigned lon
 __device__ __forceinline__ i64 thread_base(const PassParams &P, i64 outer)
 {
   const int tid = threadIdx.x;
+  if (P.n_rseg > 0) {
+    const unsigned h = (unsigned)tid >> P.B;
+    i64 off = 0;
+    for (int j = 0; j < P.n_rseg; ++j) off |= (i64)(h & P.rseg_mask[j]) << P.rseg_shift[j];
+    return outer | off | (i64)(tid & ((1 << P.B) - 1));
+  }
   return outer | __ldg(&P.rowoff[tid >> P.B]) | (i64)(tid & ((1 << P.B) - 1));
 }
 
