@@ -74,6 +74,17 @@ def msc_product(parts):
     parts = [make_msc(p) for p in parts]
     acc = parts[0]
     for nxt in parts[1:]:
+        if acc.size == 1 and nxt.size == 1:
+            # single Pauli strings (Majorana products: ~10^5 of these for SYK): plain integers
+            m1, s1, c1 = int(acc['masks'][0]), int(acc['signs'][0]), complex(acc['coeffs'][0])
+            m2, s2, c2 = int(nxt['masks'][0]), int(nxt['signs'][0]), complex(nxt['coeffs'][0])
+            c = c1 * c2
+            if bin(s1 & m2).count('1') & 1:
+                c = -c
+            acc = np.zeros(1 if c != 0 else 0, dtype=msc_dtype)
+            if c != 0:
+                acc[0] = (m1 ^ m2, s1 ^ s2, c)
+            continue
         m = acc['masks'][:, None] ^ nxt['masks'][None, :]
         s = acc['signs'][:, None] ^ nxt['signs'][None, :]
         sgn = 1 - 2 * parity(acc['signs'][:, None] & nxt['masks'][None, :])
