@@ -129,29 +129,70 @@ def oracle_problem(H, L):
     return oracle.Msc(masks, offs, H.msc['signs'], H.msc['coeffs']), oracle.Subspace({'type': 'full', 'L': L})
 
 
-def cpu_sample(omsc, osub, x, y, diag, seconds, use_diag, max_rows=None):
-    """Time the oracle port of MatMult_CPU_Fast on a bounded block range of the
-    same multiply with every host core.  Returns (seconds per full MatMult, dict)."""
+def fill_diag(omsc, osub, diag, rows, threads):
+    """diag[0:rows] with every host core (the oracle routine is serial; ctypes drops the GIL)."""
     import oracle
-    threads = os.cpu_count() or 1
-    nblk_total = osub.dim // 2048
-    nblk_cap = nblk_total if max_rows is None else max(1, min(nblk_total, max_rows // 2048))
-    probe = min(nblk_cap, max(threads * 8, 256))
+    from concurrent.futures import ThreadPoolExecutor
+    cuts = np.linspace(0, rows, threads * 4 + 1).astype(np.int64)
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda ab: oracle.precompute_diag_range(omsc, osub, diag, int(ab[0]), int(ab[1])),
+                    [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]))
 
-    def run(nblk):
+
+class CpuSampler:
+    """Times the oracle port of MatMult_CPU_Fast on a bounded block range of the same multiply with
+    every host core.  The block count is calibrated ONCE and the (step-invariant) precomputed
+    diagonal of those rows is filled ONCE, outside every timed region -- the reference computes it
+    at build_mat time, not per MatMult (operators.py:611-616)."""
+
+    def __init__(self, omsc, osub, x, y, diag, seconds, use_diag, max_rows=None, prepare=None):
+        import oracle
+        self.oracle = oracle
+        self.omsc, self.osub, self.x, self.y = omsc, osub, x, y
+        self.diag = diag if use_diag else None
+        self.threads = os.cpu_count() or 1
+        self.nblk_total = osub.dim // 2048
+        nblk_cap = self.nblk_total if max_rows is None else max(1, min(self.nblk_total, max_rows // 2048))
+        probe = min(nblk_cap, max(self.threads * 8, 256))
+        if prepare is not None:
+            prepare(probe * 2048)
         if use_diag:
-            oracle.precompute_diag_range(omsc, osub, diag, 0, nblk * 2048)
+            fill_diag(omsc, osub, diag, probe * 2048, self.threads)
+        dt, used = self._run(probe)
+        nblk = int(min(nblk_cap, max(probe, probe * seconds / max(dt, 1e-6))))
+        self.nblk = max(used, nblk - nblk % used)
+        if prepare is not None:
+            prepare(self.nblk * 2048)
+        if use_diag and self.nblk > probe:
+            fill_diag(omsc, osub, diag, self.nblk * 2048, self.threads)
+
+    def _run(self, nblk):
         t0 = time.perf_counter()
-        used = oracle.matmult_fast_range(omsc, osub, x, y, 0, nblk, diag=diag if use_diag else None, nthreads=threads)
+        used = self.oracle.matmult_fast_range(self.omsc, self.osub, self.x, self.y, 0, nblk, diag=self.diag,
+                                              nthreads=self.threads)
         return time.perf_counter() - t0, used
 
-    dt, used = run(probe)
-    nblk = int(min(nblk_cap, max(probe, probe * seconds / max(dt, 1e-6))))
-    nblk = max(used, nblk - nblk % used)
-    dt, used = run(nblk)
-    full = dt * nblk_total / nblk
-    return full, {'cores': used, 'sample': f'{nblk} of {nblk_total} blocks of 2048 rows ({nblk * 2048} rows, '
-                                           f'{dt:.2f} s wall) of the same MatMult, scaled to the full vector'}
+    def sample(self):
+        """(seconds per full MatMult, description) from one timed pass over the calibrated blocks"""
+        dt, used = self._run(self.nblk)
+        full = dt * self.nblk_total / self.nblk
+        return full, {'cores': used,
+                      'sample': f'{self.nblk} of {self.nblk_total} blocks of 2048 rows ({self.nblk * 2048} rows, '
+                                f'{dt:.2f} s wall) of the same MatMult, scaled to the full vector'}
+
+
+def workload_config(args, L, world, Hc):
+    """the `config` block: identical for both arms (the driver compares them key by key)"""
+    n = 1 << L
+    nloc = n // world
+    p = int(round(math.log2(world)))
+    return {'workload': f'L={L} {args.H} Full-space shell MatMult (BASELINE C3), one step = one y=Hx',
+            'L': L, 'rows': n, 'rows_per_gpu': nloc, 'vector_gib_per_gpu': nloc * 16 / 2**30,
+            'unique_masks': int(Hc.nnz), 'nterms': int(Hc.nterms),
+            'precompute_diagonal': not args.no_precompute_diagonal,
+            'parallelism': 'single GPU' if world == 1 else f'state vector sharded by the top {p} index bits, '
+                                                           'cross-shard masks over NVLink',
+            'l2_policy': 'inputs (16 GiB/GPU) far exceed the 126 MB L2; no flush needed'}
 
 
 def run_reference(args, rank, world):
@@ -174,21 +215,32 @@ def run_reference(args, rank, world):
     y = reserve(n, np.complex128)
     diag = reserve(n if use_diag else 1, np.float64)
     per_step = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
-    threads = os.cpu_count() or 1
-    span = 1 << 21
-    while span < n and span * 2 / (8e6 * threads) < 4 * per_step:   # generous bound on rows one sample can reach
-        span *= 2
-    base = ((np.arange(min(span, 1 << 22)) % 1021) - 510.0) / 510.0 * (1 + 0.5j)
-    for m in np.unique(omsc.masks):
-        start = int(m) & ~(span - 1)
-        for s in range(start, min(start + span, n), base.size):
-            x[s:s + base.size] = base[:min(base.size, n - s)]
+    base = ((np.arange(1 << 20) % 1021) - 510.0) / 510.0 * (1 + 0.5j)
+    filled = set()
+
+    def prepare(rows):
+        # rows [0, rows) read x[i ^ mask]: one window of `span` entries per unique mask
+        span = 1 << 20
+        while span < rows:
+            span *= 2
+        span = min(span, n)
+        for m in np.unique(omsc.masks):
+            start = int(m) & ~(span - 1)
+            for s in range(start, min(start + span, n), base.size):
+                if s not in filled:
+                    filled.add(s)
+                    x[s:s + base.size] = base[:min(base.size, n - s)]
+
     info = None
+    # bounded sample: at most 2^29 rows (2^28 for the sharded sizes, whose high masks each need their own
+    # window of x in host memory)
+    sampler = CpuSampler(omsc, osub, x, y, diag, per_step, use_diag, max_rows=1 << (29 if n <= 1 << 30 else 28),
+                         prepare=prepare)
     for _ in range(args.warmup):
-        cpu_sample(omsc, osub, x, y, diag, per_step, use_diag, max_rows=span)
+        sampler.sample()
     times = []
     for _ in range(args.steps):
-        full, info = cpu_sample(omsc, osub, x, y, diag, per_step, use_diag, max_rows=span)
+        full, info = sampler.sample()
         times.append(full)
     sec = float(np.mean(times))
     value = (n / ROWS_UNIT) / sec
@@ -196,10 +248,9 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'c128 (f64 complex)', 'data': 'synthetic',
-        'config': {'workload': f'L={L} {args.H} Full-space shell MatMult (BASELINE C3), one step = one y=Hx',
-                   'L': L, 'rows': n, 'precompute_diagonal': use_diag,
-                   'arm': 'CPU port of MatMult_CPU_Fast (oracle/dnm_oracle.c), pthreads over all host cores; '
-                          'the real reference needs PETSc/SLEPc/MPI, absent from this image'},
+        'config': workload_config(args, L, world, H),
+        'arm': 'CPU port of MatMult_CPU_Fast (oracle/dnm_oracle.c), pthreads over all host cores; '
+               'the real reference needs PETSc/SLEPc/MPI, absent from this image',
         'cpu_baseline': {'value': value, 'unit': UNIT, 'kind': 'port', **info},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -417,7 +468,7 @@ def run_ours(args, rank, world, local_rank):
         omsc, osub = oracle_problem(H, L)
         use_diag = not args.no_precompute_diagonal
         diag = np.empty(n if use_diag else 1, dtype=np.float64)
-        full_sec, info = cpu_sample(omsc, osub, xh, yh, diag, args.cpu_seconds, use_diag)
+        full_sec, info = CpuSampler(omsc, osub, xh, yh, diag, args.cpu_seconds, use_diag).sample()
         cpu = {'value': units / full_sec, 'unit': UNIT, 'kind': 'port', **info}
         del diag
     for ptr in host:
@@ -433,13 +484,7 @@ def run_ours(args, rank, world, local_rank):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'c128 (f64 complex)', 'data': 'synthetic',
-            'config': {'workload': f'L={L} {args.H} Full-space shell MatMult (BASELINE C3), one step = one y=Hx',
-                       'L': L, 'rows': n, 'rows_per_gpu': nloc, 'vector_gib_per_gpu': nloc * 16 / 2**30,
-                       'unique_masks': int(mat_info_cache['unique_masks']), 'nterms': int(mat_info_cache['nterms']),
-                       'precompute_diagonal': not args.no_precompute_diagonal,
-                       'parallelism': 'single GPU' if world == 1 else f'state vector sharded by the top {p} index bits, '
-                                                                      'peer loads over NVLink for cross-shard masks',
-                       'l2_policy': 'inputs (16 GiB/GPU) far exceed the 126 MB L2; no flush needed'},
+            'config': workload_config(args, L, world, H),
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
             'extras': extras,
         }
@@ -448,8 +493,6 @@ def run_ours(args, rank, world, local_rank):
         dist.barrier()
         dist.destroy_process_group()
 
-
-mat_info_cache = {}
 
 _RESULT_FD = None
 
@@ -490,12 +533,6 @@ def main():
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
                '--master-addr', '127.0.0.1', '--master-port', '29511', os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    # unique_masks / nterms for the config block come from the host MSC (no GPU needed)
-    from dynamite_b200.hamiltonians import build_hamiltonian
-    p = int(round(math.log2(world)))
-    Hc = build_hamiltonian(args.H, args.L or 30 + p)
-    mat_info_cache['unique_masks'] = Hc.nnz
-    mat_info_cache['nterms'] = Hc.nterms
     run_ours(args, rank, world, local_rank)
 
 

@@ -155,6 +155,8 @@ struct dnm_mat_s {
   int tile_bits = 0;    // 0 auto
   int tile_rows = 0;    // rows per thread in the tiled kernel: 0 auto, 8 or 16
   int pipeline = 0;     // pipelined persistent tiled kernel: 0 auto, 1 on, 2 off
+  int jit = -1;         // operator-specialised (NVRTC) kernels for lean tiled passes: -1 auto, 0 off, 1 on
+  int far_bits = -1;    // outer positions a tiled pass may serve through the L2 (FAR masks): -1 auto
   int verbose = 0;
   dnm::TiledPlan *tiled = nullptr;
   int launches_per_mult = 0;

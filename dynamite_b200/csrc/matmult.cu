@@ -563,6 +563,14 @@ extern "C" int dnm_mat_set_option(dnm_mat_t A, const char *key, int64_t value)
     DNM_REQUIRE(value >= 0 && value <= 2, DNM_ERR_ARG, "pipeline must be 0 (auto), 1 (on) or 2 (off)");
     A->pipeline = (int)value;
     tiled_free(A);
+  } else if (!strcmp(key, "jit")) {
+    DNM_REQUIRE(value >= -1 && value <= 1, DNM_ERR_ARG, "jit must be -1 (auto), 0 (off) or 1 (on)");
+    A->jit = (int)value;
+    tiled_free(A);
+  } else if (!strcmp(key, "far_bits")) {
+    DNM_REQUIRE(value >= -1 && value <= 16, DNM_ERR_ARG, "far_bits must be -1 (auto) or in [0,16]");
+    A->far_bits = (int)value;
+    tiled_free(A);
   } else if (!strcmp(key, "verbose")) {
     A->verbose = (int)value;
   } else {
@@ -586,6 +594,7 @@ extern "C" int dnm_mat_get_info(dnm_mat_t A, const char *key, double *value)
   else if (!strcmp(key, "compulsory_bytes")) *value = 2.0 * nloc * 16.0 + (A->d_diag ? 8.0 * nloc : 0.0);
   else if (!strcmp(key, "launches_per_mult")) *value = A->launches_per_mult;
   else if (!strcmp(key, "has_diag")) *value = A->d_diag ? 1.0 : 0.0;
+  else if (!strcmp(key, "jit_passes")) *value = tiled_jit_passes(A);
   else DNM_REQUIRE(false, DNM_ERR_ARG, "unknown info key '%s'", key);
   DNM_API_END
 }

@@ -25,6 +25,7 @@
 #include <string>
 #include <memory>
 
+#include "jit.h"
 #include "tiled_kernel.cuh"
 #include "vecops.cuh"
 
@@ -173,10 +174,12 @@ struct Pass {
   int T = 0;
   int R = 16;
   int peer_xor = 0;  // x is read from rank ^ peer_xor
-  bool pipe = false; // run with the pipelined persistent kernel (k_tiled_ring)
   int nterms = 0;
   int nmasks = 0;
+  int nfar = 0;      // masks served through the L2 window (FAR groups)
   i64 wbits = 0;     // window bit positions
+  std::vector<int> W;               // the same as a list: W[j] = index bit of window coordinate j
+  const jit::Kernel *jk = nullptr;  // operator-specialised kernel of this pass (owned by TiledPlan::jit)
   std::vector<void *> owned;
 };
 
@@ -188,14 +191,9 @@ struct Direct {
 
 }  // namespace
 
-// A launch unit: one pass, or several consecutive passes fused through the L2 (k_tiled_fused)
+// A launch unit: one pass
 struct Unit {
   std::vector<int> passes;  // indices into TiledPlan::passes
-  bool fused = false;
-  FusedParams fp{};
-  int *d_sync = nullptr;    // done counters followed by the ticket (8-byte aligned at the end)
-  size_t sync_bytes = 0;
-  int grid = 0;
 };
 
 struct TiledPlan {
@@ -212,6 +210,7 @@ struct TiledPlan {
   PassParams *d_batch = nullptr;  // all passes' parameters, when the whole product runs as one batched launch
   size_t batch_stage_bytes = 0;   // shared memory for the largest staged term table among them
   int batch_T = 0, batch_R = 0;
+  jit::Module *jit = nullptr;  // generated kernels of the lean passes
   bool dma = false;          // remote shards are staged by the copy engines while the local passes run
   cplx *stage[2] = {nullptr, nullptr};
   cudaEvent_t ev_staged[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
@@ -230,8 +229,7 @@ struct TiledPlan {
     for (auto &d : directs)
       for (void *q : d.owned) cudaFree(q);
     for (void *q : all.owned) cudaFree(q);
-    for (auto &u : units)
-      if (u.d_sync) cudaFree(u.d_sync);
+    delete jit;
     if (y_remote) cudaFree(y_remote);
     if (d_batch) cudaFree(d_batch);
     for (int b = 0; b < 2; ++b) {
@@ -356,14 +354,17 @@ void fill_segments(PassParams &p)
       return;
     }
     p.seg_mask[p.n_seg] = (((unsigned long long)1 << (e - k)) - 1ull) << k;
-    p.seg_shift[p.n_seg] = (unsigned char)(p.outer_pos[k] - k);
+    p.seg_shift[p.n_seg] = (signed char)((int)p.outer_pos[k] - k);
     ++p.n_seg;
     k = e;
   }
 }
 
+// `masks` = the masks inside the window followed by `nfar` FAR masks, which also flip outer
+// positions inside `farbits` (the pass's L2 window: those positions become the lowest tile-number
+// bits, so the tiles a far mask connects run at the same time and its operand is an L2 hit).
 Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &W, int T, int R, int B, int nloc,
-               int accumulate)
+               int accumulate, size_t nfar = 0, i64 farbits = 0)
 {
   Pass ps;
   ps.T = T;
@@ -461,7 +462,11 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
     }
     return rp;
   };
-  for (const NMask *nm : masks) {
+  std::vector<unsigned long long> gfar;  // per group: the local flip mask of a FAR group, else 0
+  for (size_t mi = 0; mi < masks.size(); ++mi) {
+    const NMask *nm = masks[mi];
+    gfar.resize(lam.size(), 0);
+    const bool is_far = mi >= masks.size() - nfar;
     const u32 l = extract(nm->mask & lmask);
     if (allow_tables && getenv("DNM_NO_CTABLE") == nullptr) {
       // masks with real AND imaginary terms: one joint basis, one table of complex coefficients,
@@ -547,6 +552,7 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
           t2.push_back((u16)sw.size());
           pat.push_back(0);
           kp.push_back((u8)(kind | (PATH_PAIR << 1)));
+          gfar.push_back(is_far ? (unsigned long long)(nm->mask & lmask) : 0ull);
           continue;
         }
       }
@@ -616,6 +622,7 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
     }
   }
   DNM_REQUIRE(sw.size() < 65535, DNM_ERR_UNSUPPORTED, "too many terms in one pass (%zu)", sw.size());
+  gfar.resize(lam.size(), 0);
 
   std::vector<i64> rowoff((size_t)1 << (T - B));
   for (size_t h = 0; h < rowoff.size(); ++h) {
@@ -647,8 +654,11 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
   ps.p.B = B;
   ps.p.accumulate = accumulate;
   ps.p.n_outer = 0;
+  ps.p.far_bits = popc64(farbits);
   for (int b = 0; b < nloc; ++b)
-    if (!((wbits >> b) & 1)) ps.p.outer_pos[ps.p.n_outer++] = (unsigned char)b;
+    if ((farbits >> b) & 1) ps.p.outer_pos[ps.p.n_outer++] = (unsigned char)b;
+  for (int b = 0; b < nloc; ++b)
+    if (!(((wbits | farbits) >> b) & 1)) ps.p.outer_pos[ps.p.n_outer++] = (unsigned char)b;
   fill_segments(ps.p);
   ps.p.lam = up(lam, ps.owned);
   ps.p.t0 = up(t0, ps.owned);
@@ -672,6 +682,8 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
   ps.nmasks = (int)masks.size();
   ps.nterms = (int)sw.size();
   ps.wbits = wbits;
+  ps.W = W;
+  ps.nfar = (int)nfar;
   // large passes stage csign/sw/rb (16 B per term) in shared memory when that still leaves two tiles per SM
   ps.p.staged = ((any_table || !(ps.p.ngroups <= SMALL_GROUPS && ps.nterms <= SMALL_TERMS)) && (size_t)ps.nterms * 16 <= 40 * 1024 &&
                  getenv("DNM_NO_STAGE") == nullptr) ? 1 : 0;
@@ -695,12 +707,15 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
     bool lean = R <= 8;
     for (int g = 0; g < ps.p.ngroups && lean; ++g) lean = (kp[g] >> 1) == PATH_PAIR && t0[g] == 2 * g;
     if (lean)
-      for (int g = 0; g < ps.p.ngroups; ++g)
+      for (int g = 0; g < ps.p.ngroups; ++g) {
         ps.st.gd[g] = make_uint4(lam[g], sw[2 * g], sw[2 * g + 1],
-                                 (rb[2 * g] & 0xffu) | ((rb[2 * g + 1] & 0xffu) << 8) | ((u32)(kp[g] & 1) << 16));
+                                 (rb[2 * g] & 0xffu) | ((rb[2 * g + 1] & 0xffu) << 8) | ((u32)(kp[g] & 1) << 16) |
+                                     (gfar[g] ? (1u << 17) : 0u));
+        ps.st.far[g] = gfar[g];
+      }
     if (lean && getenv("DNM_NO_CPLX") == nullptr)
       for (int g = 0; g + 1 < ps.p.ngroups; ++g) {
-        const bool plain_pair = (ps.st.gd[g].w & 0xffffu) == 0 && (ps.st.gd[g + 1].w & 0xffffu) == 0;
+        const bool plain_pair = (ps.st.gd[g].w & 0xffffu) == 0 && (ps.st.gd[g + 1].w & 0xffffu) == 0 && !gfar[g] && !gfar[g + 1];
         if (lam[g] == lam[g + 1] && !(kp[g] & 1) && (kp[g + 1] & 1) && plain_pair) {
           ps.st.gd[g].x |= 0x80000000u;
           ++g;
@@ -713,8 +728,22 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
 }
 
 // Greedy window cover of one partner group's masks.
+// a mask the lean group loop can serve: at most two distinct sign masks per (real | imaginary) part
+bool pair_eligible(const NMask *nm)
+{
+  for (int kind = 0; kind < 2; ++kind) {
+    std::vector<i64> uniq;
+    for (const NTerm &t : nm->terms) {
+      if ((int)t.imag != kind) continue;
+      if (std::find(uniq.begin(), uniq.end(), t.sign) == uniq.end()) uniq.push_back(t.sign);
+    }
+    if (uniq.size() > 2) return false;
+  }
+  return true;
+}
+
 void plan_group(TiledPlan &plan, std::vector<const NMask *> remaining, int peer_xor, int T, int R, int B,
-                bool first_group, int verbose)
+                bool first_group, int verbose, int fmax = 0)
 {
   const int nloc = plan.nloc;
   const i64 lmask = ((i64)1 << nloc) - 1;
@@ -768,11 +797,55 @@ void plan_group(TiledPlan &plan, std::vector<const NMask *> remaining, int peer_
       if ((W >> b) & 1) Wpos.push_back(b);
     // masks are kept in ascending order inside a pass
     std::sort(chosen.begin(), chosen.end(), [](const NMask *a, const NMask *b) { return a->mask < b->mask; });
-    Pass ps = make_pass(chosen, Wpos, T, R, B, nloc, wrote ? 1 : 0);
+    // FAR masks: also flip up to fmax outer positions (the pass's L2 window); the operand comes from
+    // global memory while the tiles of one far-bit block are in flight together (lean passes only)
+    i64 F = 0;
+    std::vector<const NMask *> farm;
+    std::vector<char> taken_far(remaining.size(), 0);
+    bool chosen_ok = R <= 8;
+    for (const NMask *nm : chosen) chosen_ok = chosen_ok && pair_eligible(nm);
+    if (fmax > 0 && chosen_ok) {
+      size_t groups = 0;
+      for (const NMask *nm : chosen) groups += 2;
+      for (;;) {
+        int best = -1, best_new = 1 << 30;
+        i64 best_bits = 0;
+        for (size_t k = 0; k < remaining.size(); ++k) {
+          if (taken[k] || taken_far[k] || !pair_eligible(remaining[k])) continue;
+          const i64 extra = (remaining[k]->mask & lmask) & ~(W | F);
+          const int nnew = popc64(extra);
+          if (popc64(F) + nnew > fmax) continue;
+          if (nnew < best_new || (nnew == best_new && extra < best_bits)) {
+            best = (int)k;
+            best_new = nnew;
+            best_bits = extra;
+          }
+        }
+        if (best < 0 || groups + 2 > (size_t)SMALL_GROUPS || 2 * (groups + 2) > (size_t)SMALL_TERMS) break;
+        taken_far[best] = 1;
+        farm.push_back(remaining[best]);
+        F |= best_bits;
+        groups += 2;
+      }
+      std::sort(farm.begin(), farm.end(), [](const NMask *a, const NMask *b) { return a->mask < b->mask; });
+    }
+    std::vector<const NMask *> both(chosen);
+    both.insert(both.end(), farm.begin(), farm.end());
+    Pass ps = make_pass(both, Wpos, T, R, B, nloc, wrote ? 1 : 0, farm.size(), F);
+    if (!farm.empty() && !(ps.small && ps.p.lean)) {
+      // the far path only exists in the lean group loop: plan this pass without it
+      for (void *q : ps.owned) cudaFree(q);
+      farm.clear();
+      std::fill(taken_far.begin(), taken_far.end(), 0);
+      F = 0;
+      ps = make_pass(chosen, Wpos, T, R, B, nloc, wrote ? 1 : 0);
+    }
+    for (size_t k = 0; k < remaining.size(); ++k) taken[k] = taken[k] || taken_far[k];
     ps.peer_xor = peer_xor;
     if (verbose)
-      fprintf(stderr, "[dnm] pass %zu: peer^%d window=0x%llx masks=%d terms=%d %s\n", plan.passes.size(), peer_xor,
-              (unsigned long long)W, ps.nmasks, ps.nterms, wrote ? "accumulate" : "write");
+      fprintf(stderr, "[dnm] pass %zu: peer^%d window=0x%llx far=0x%llx masks=%d (%d far) terms=%d %s\n",
+              plan.passes.size(), peer_xor, (unsigned long long)W, (unsigned long long)F, ps.nmasks, ps.nfar, ps.nterms,
+              wrote ? "accumulate" : "write");
     plan.passes.push_back(std::move(ps));
     wrote = true;
     std::vector<const NMask *> rest;
@@ -815,85 +888,6 @@ void launch_tiled(const Pass &ps, const cplx *x, cplx *y, const double *diag, i6
   else launch_tiled_v<T, R, false>(ps, x, y, diag, ntiles);
 }
 
-// ---- pipelined persistent kernel (k_tiled_ring) ----
-// shared memory left for staged term tables next to the three half-tile buffers
-template <int T>
-constexpr size_t pipe_table_room()
-{
-  // per CTA: 1 KiB reserved by the system, ~1 KiB of static shared memory; at most 227 KiB per block
-  constexpr long long share = 233472 / RingCfg<T>::CTAS;
-  constexpr long long cap = share < 232448 ? share : 232448;
-  constexpr long long room = cap - 2048 - (long long)RingCfg<T>::RING_BYTES;
-  return room > 0 ? (size_t)room : 0;
-}
-
-size_t pipe_room(int T)
-{
-  switch (T) {
-    case 10: return pipe_table_room<10>();
-    case 11: return pipe_table_room<11>();
-    case 12: return pipe_table_room<12>();
-    case 13: return pipe_table_room<13>();
-    default: return 0;
-  }
-}
-
-bool pipe_eligible(const Pass &ps)
-{
-  return ps.R == 8 && ps.T >= 10 && ps.T <= 13 && ps.p.accumulate != 2 &&
-         (!ps.p.staged || (size_t)ps.nterms * 16 <= pipe_room(ps.T));
-}
-
-// work tickets of the persistent kernels: a small ring so that launches on different streams
-// never share a counter
-unsigned long long *next_ticket(cudaStream_t st)
-{
-  static unsigned long long *d_tickets = nullptr;
-  static int cursor = 0;
-  constexpr int N = 64;
-  if (!d_tickets) DNM_CHECK_CUDA(cudaMalloc(&d_tickets, N * sizeof(unsigned long long)));
-  unsigned long long *t = d_tickets + (cursor++ % N);
-  DNM_CHECK_CUDA(cudaMemsetAsync(t, 0, sizeof(unsigned long long), st));
-  return t;
-}
-
-template <int T, bool SMALL>
-void launch_pipe_v(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
-{
-  static bool attr_set = false;
-  const size_t smem = RingCfg<T>::RING_BYTES + (ps.p.staged ? (size_t)ps.nterms * 16 : 0);
-  if (!attr_set) {
-    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_ring<T, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(RingCfg<T>::RING_BYTES + pipe_table_room<T>())));
-    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_ring<T, SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set = true;
-  }
-  i64 grid = std::min<i64>(ntiles, (i64)G.sm_count * RingCfg<T>::CTAS);
-  if (const char *e = getenv("DNM_PIPE_CTAS"))  // tests: few CTAs, many tiles each
-    if (atoi(e) > 0) grid = std::min<i64>(grid, atoi(e));
-  cudaStream_t st = launch_stream();
-  unsigned long long *ticket = next_ticket(st);
-  k_tiled_ring<T, SMALL><<<(unsigned)grid, RingCfg<T>::NT, smem, st>>>(ps.p, ps.st, x, y, diag, (unsigned long long)ntiles,
-                                                                    ticket);
-  count_launch();
-  DNM_CHECK_CUDA(cudaGetLastError());
-}
-
-void launch_pipe(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
-{
-#define DNM_PIPE_CASE(TT)                                                      \
-  if (ps.T == TT) {                                                            \
-    if (ps.small) return launch_pipe_v<TT, true>(ps, x, y, diag, ntiles);      \
-    return launch_pipe_v<TT, false>(ps, x, y, diag, ntiles);                   \
-  }
-  DNM_PIPE_CASE(10)
-  DNM_PIPE_CASE(11)
-  DNM_PIPE_CASE(12)
-  DNM_PIPE_CASE(13)
-#undef DNM_PIPE_CASE
-  DNM_REQUIRE(false, DNM_ERR_INTERNAL, "no pipelined kernel for T=%d", ps.T);
-}
-
 // rows per thread for a tile size: 16 by default (8 on request) where the CTA stays >= 64 threads
 int rows_for(int T, int want)
 {
@@ -904,7 +898,11 @@ int rows_for(int T, int want)
 
 void launch_pass(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
 {
-  if (ps.pipe) return launch_pipe(ps, x, y, diag, ntiles);
+  if (ps.jk) {
+    jit::launch(*ps.jk, (unsigned long long)ntiles, launch_stream(), x, y, diag, (long long)ps.p.rank_bits);
+    count_launch();
+    return;
+  }
 #define DNM_TILE_CASE(TT, RR) \
   if (ps.T == TT && ps.R == RR) return launch_tiled<TT, RR>(ps, x, y, diag, ntiles);
   DNM_TILE_CASE(8, 4)
@@ -926,43 +924,6 @@ int direct_grid(i64 rows)
   const i64 want = (rows + 255) / 256;
   const i64 cap = (i64)G.sm_count * 16;
   return (int)std::max<i64>(1, std::min(want, cap));
-}
-
-template <int T, int R>
-void launch_fused_tr(const Unit &u, const cplx *x, cplx *y, const double *diag, int ctas_per_sm)
-{
-  static int occ = 0;
-  const size_t smem = sizeof(double2) << T;
-  if (!occ) {
-    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_fused<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DNM_CHECK_CUDA(cudaFuncSetAttribute(k_tiled_fused<T, R>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    DNM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tiled_fused<T, R>, TileCfg<T, R>::NT, smem));
-    if (occ < 1) occ = 1;
-  }
-  DNM_CHECK_CUDA(cudaMemsetAsync(u.d_sync, 0, u.sync_bytes, launch_stream()));
-  const unsigned long long cap = (unsigned long long)G.sm_count * (ctas_per_sm > 0 ? std::min(ctas_per_sm, occ) : occ);
-  const unsigned grid = (unsigned)std::min<unsigned long long>(cap, u.fp.nitems);
-  k_tiled_fused<T, R><<<grid, TileCfg<T, R>::NT, smem, launch_stream()>>>(u.fp, x, y, diag);
-  count_launch();
-  DNM_CHECK_CUDA(cudaGetLastError());
-}
-
-void launch_fused(const Unit &u, int T, int R, const cplx *x, cplx *y, const double *diag, int ctas_per_sm = 0)
-{
-#define DNM_FUSE_CASE(TT, RR) \
-  if (T == TT && R == RR) return launch_fused_tr<TT, RR>(u, x, y, diag, ctas_per_sm);
-  DNM_FUSE_CASE(8, 4)
-  DNM_FUSE_CASE(9, 8)
-  DNM_FUSE_CASE(10, 8)
-  DNM_FUSE_CASE(10, 16)
-  DNM_FUSE_CASE(11, 8)
-  DNM_FUSE_CASE(11, 16)
-  DNM_FUSE_CASE(12, 8)
-  DNM_FUSE_CASE(12, 16)
-  DNM_FUSE_CASE(13, 8)
-  DNM_FUSE_CASE(13, 16)
-#undef DNM_FUSE_CASE
-  DNM_REQUIRE(false, DNM_ERR_INTERNAL, "no fused kernel for T=%d R=%d", T, R);
 }
 
 template <int T, int R>
@@ -1006,77 +967,13 @@ void launch_batch(const TiledPlan &plan, const cplx *x, cplx *y, const double *d
   DNM_REQUIRE(false, DNM_ERR_INTERNAL, "no batched kernel for T=%d R=%d", plan.batch_T, plan.batch_R);
 }
 
-// Group consecutive local passes whose windows together span few enough bits for their
-// chunk (x and y) to stay in the L2 between passes.
-void build_units(TiledPlan &plan, int verbose)
+// one launch unit per pass
+void build_units(TiledPlan &plan, int)
 {
-  // Off by default: measured on B200 (profiles/r01_fusion_experiment.md) the fused persistent kernel
-  // halves DRAM traffic but is dependency/latency bound and slower than the per-pass kernels.
-  // DNM_FUSE_BITS=18 enables it (2^18 amplitudes = 4 MiB of x + 4 MiB of y per chunk).
-  int fuse_bits = 0;
-  int lag = 2;
-  if (const char *e = getenv("DNM_FUSE_BITS")) fuse_bits = atoi(e);
-  if (const char *e = getenv("DNM_FUSE_LAG")) lag = std::max(1, atoi(e));
-  const int nloc = plan.nloc;
-  size_t i = 0;
-  while (i < plan.passes.size()) {
+  for (size_t i = 0; i < plan.passes.size(); ++i) {
     Unit u;
     u.passes.push_back((int)i);
-    const Pass &first = plan.passes[i];
-    i64 U = first.wbits;
-    size_t j = i + 1;
-    if (fuse_bits > 0 && first.small && first.peer_xor == 0) {
-      while (j < plan.passes.size() && (int)u.passes.size() < MAX_FUSED_PASSES) {
-        const Pass &nx = plan.passes[j];
-        if (!nx.small || nx.peer_xor != 0 || nx.T != first.T || nx.R != first.R) break;
-        if (popc64(U | nx.wbits) > std::min(fuse_bits, nloc)) break;
-        U |= nx.wbits;
-        u.passes.push_back((int)j);
-        ++j;
-      }
-    }
-    // local small passes always run in the persistent kernel (it prefetches through the L2),
-    // fused when more than one pass shares a chunk
-    const bool remote_persistent = plan.overlap && first.small && first.peer_xor != 0;
-    if (u.passes.size() > 1 || remote_persistent ||
-        (fuse_bits > 0 && first.small && first.peer_xor == 0 && getenv("DNM_PERSISTENT"))) {
-      const int ubits = popc64(U);
-      u.fused = true;
-      FusedParams &fp = u.fp;
-      fp.npasses = (int)u.passes.size();
-      fp.lag = lag;
-      fp.log_tiles = ubits - first.T;
-      fp.nchunks = (long long)1 << (nloc - ubits);
-      fp.nitems = (unsigned long long)(fp.nchunks + (long long)(fp.npasses - 1) * lag) * fp.npasses << fp.log_tiles;
-      fp.diag_pass = -1;
-      fp.prefetch = first.peer_xor == 0 ? 1 : 0;
-      for (int k = 0; k < fp.npasses; ++k) {
-        const Pass &ps = plan.passes[u.passes[k]];
-        fp.p[k] = ps.p;
-        fp.s[k] = ps.st;
-        // tile id = (tile within chunk) | (chunk << log_tiles): first the chunk-internal positions
-        // outside this pass's window, then the positions outside the chunk (same order for every pass)
-        int pos = 0;
-        for (int b = 0; b < nloc; ++b)
-          if (((U >> b) & 1) && !((ps.wbits >> b) & 1)) fp.p[k].outer_pos[pos++] = (unsigned char)b;
-        for (int b = 0; b < nloc; ++b)
-          if (!((U >> b) & 1)) fp.p[k].outer_pos[pos++] = (unsigned char)b;
-        fp.p[k].n_outer = pos;
-        fill_segments(fp.p[k]);
-        if (plan.use_diag && u.passes[k] == 0) fp.diag_pass = k;
-      }
-      const size_t nflags = (size_t)(fp.npasses - 1) * (size_t)fp.nchunks;
-      const size_t flag_bytes = (nflags * sizeof(int) + 7) / 8 * 8;
-      u.sync_bytes = flag_bytes + sizeof(unsigned long long);
-      DNM_CHECK_CUDA(cudaMalloc(&u.d_sync, u.sync_bytes));
-      fp.done = u.d_sync;
-      fp.ticket = (unsigned long long *)((char *)u.d_sync + flag_bytes);
-      if (verbose)
-        fprintf(stderr, "[dnm] fused unit: passes %d..%d, chunk bits %d (%lld chunks, %d tiles each), lag %d\n",
-                u.passes.front(), u.passes.back(), ubits, fp.nchunks, 1 << fp.log_tiles, lag);
-    }
     plan.units.push_back(std::move(u));
-    i = j;
   }
 }
 
@@ -1183,13 +1080,20 @@ std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &mas
     plan->dma = groups.size() > 1 && mode == "dma";
     plan->overlap = groups.size() > 1 && mode == "peer_overlap";
     bool first_local = true, first_remote = true;
+    // L2 window (FAR masks): option far_bits, -1 = auto
+    int fmax = A->far_bits;
+    if (fmax < 0) {
+      fmax = 0;
+      if (const char *e = getenv("DNM_FAR_BITS")) fmax = atoi(e);
+    }
+    fmax = std::max(0, std::min(fmax, nloc - T));
     for (auto &kv : groups) {
       if (kv.first == 0) {
-        plan_group(*plan, kv.second, kv.first, T, R, B, first_local, verbose);
+        plan_group(*plan, kv.second, kv.first, T, R, B, first_local, verbose, fmax);
         first_local = false;
       } else {
         const size_t before = plan->passes.size(), dbefore = plan->directs.size();
-        plan_group(*plan, kv.second, kv.first, T, R, B, plan->overlap && first_remote, verbose);
+        plan_group(*plan, kv.second, kv.first, T, R, B, plan->overlap && first_remote, verbose, fmax);
         first_remote = false;
         plan->any_remote = true;
         // partial staging is only safe where a zero coefficient never touches the operand (lean passes)
@@ -1209,7 +1113,6 @@ std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &mas
   // pipeline: 1 = the ring kernel wherever it exists; 0 (auto) and 2 = one tile per CTA.  Measured on
   // B200 (profiles/r01_ring_experiment.md): the arithmetic phase is bound by shared-memory
   // bandwidth, not by the fetches the ring hides, and the ring kernel is 5-20 % slower.
-  for (Pass &ps : plan->passes) ps.pipe = A->pipeline == 1 && pipe_eligible(ps);
   build_units(*plan, verbose);
   double cost = 0.0;
   for (const Unit &u : plan->units) {
@@ -1277,6 +1180,41 @@ TiledPlan *build_plan(dnm_mat_s *A)
       best->batch_R = p0.R;
     }
   }
+  // Operator-specialised kernels for the lean passes (jit.h): on by default for vectors that leave
+  // the L2 (the generic kernel is kept for small problems, where compiling would dominate).
+  const bool want_jit = A->jit == 1 || (A->jit < 0 && getenv("DNM_NO_JIT") == nullptr && best && best->nloc >= 22);
+  if (best && want_jit && !best->d_batch) {
+    std::vector<jit::PassDesc> descs;
+    std::vector<size_t> which;
+    for (size_t k = 0; k < best->passes.size(); ++k) {
+      const Pass &ps = best->passes[k];
+      if (!(ps.small && ps.p.lean && ps.R == 8 && ps.T >= 9 && ps.p.accumulate != 2)) continue;
+      jit::PassDesc d;
+      d.p = &ps.p;
+      d.st = &ps.st;
+      d.T = ps.T;
+      d.W = ps.W;
+      descs.push_back(d);
+      which.push_back(k);
+    }
+    if (!descs.empty()) {
+      std::string log;
+      const std::string src = jit::generate(descs, 0);
+      if (const char *dump = getenv("DNM_JIT_DUMP")) {
+        if (FILE *f = fopen(dump, "w")) {
+          fwrite(src.data(), 1, src.size(), f);
+          fclose(f);
+        }
+      }
+      best->jit = jit::compile(src, descs, log, true);
+      if (best->jit) {
+        for (size_t k = 0; k < which.size(); ++k) best->passes[which[k]].jk = &best->jit->kernels[k];
+        if (A->verbose) fprintf(stderr, "[dnm] %zu generated kernels (%zu bytes of source)\n", which.size(), src.size());
+      } else if (A->verbose || A->jit == 1) {
+        fprintf(stderr, "[dnm] generated kernels unavailable, using the generic tiled kernel: %s\n", log.c_str());
+      }
+    }
+  }
   DNM_CHECK_CUDA(cudaStreamSynchronize(G.stream));
   return best.release();
 }
@@ -1301,6 +1239,14 @@ void tiled_free(dnm_mat_s *A)
 {
   delete A->tiled;
   A->tiled = nullptr;
+}
+
+int tiled_jit_passes(dnm_mat_s *A)
+{
+  int n = 0;
+  if (A->tiled)
+    for (const Pass &ps : A->tiled->passes) n += ps.jk ? 1 : 0;
+  return n;
 }
 
 int tiled_passes(dnm_mat_s *A) { return A->tiled ? (int)(A->tiled->passes.size() + A->tiled->directs.size()) : 0; }
@@ -1353,8 +1299,7 @@ void tiled_mult(dnm_mat_s *A, dnm_vec_t xv, dnm_vec_t yv)
       const Pass &ps = plan.passes[u.passes.front()];
       if (ps.peer_xor != 0) continue;
       const double *diag = (first && plan.use_diag) ? A->d_diag : nullptr;
-      if (u.fused) launch_fused(u, ps.T, ps.R, xv->d, y, plan.use_diag ? A->d_diag : nullptr);
-      else launch_pass(ps, xv->d, y, diag, nloc_rows >> ps.T);
+      launch_pass(ps, xv->d, y, diag, nloc_rows >> ps.T);
       first = false;
       ++launches;
     }
@@ -1392,8 +1337,7 @@ void tiled_mult(dnm_mat_s *A, dnm_vec_t xv, dnm_vec_t yv)
       for (const Unit &u : plan.units) {
         const Pass &ps = plan.passes[u.passes.front()];
         if (ps.peer_xor != partners[gi]) continue;
-        if (u.fused) launch_fused(u, ps.T, ps.R, plan.stage[b], y, nullptr);
-        else launch_pass(ps, plan.stage[b], y, nullptr, nloc_rows >> ps.T);
+        launch_pass(ps, plan.stage[b], y, nullptr, nloc_rows >> ps.T);
         ++launches;
       }
       for (const Direct &d : plan.directs) {
@@ -1418,16 +1362,13 @@ void tiled_mult(dnm_mat_s *A, dnm_vec_t xv, dnm_vec_t yv)
     // fork: the side stream starts once x is globally ready
     DNM_CHECK_CUDA(cudaEventRecord(G.ev_fork, G.stream));
     DNM_CHECK_CUDA(cudaStreamWaitEvent(G.stream2, G.ev_fork, 0));
-    int remote_ctas = 1;
-    if (const char *e = getenv("DNM_REMOTE_CTAS")) remote_ctas = std::max(1, atoi(e));
     g_launch_stream = G.stream2;
     try {
       for (const Unit &u : plan.units) {
         const Pass &ps = plan.passes[u.passes.front()];
         if (ps.peer_xor == 0) continue;
         // a few resident CTAs per SM keep the NVLink busy and leave the rest of the SM to the local passes
-        if (u.fused) launch_fused(u, ps.T, ps.R, source(ps.peer_xor), yr, nullptr, remote_ctas);
-        else launch_pass(ps, source(ps.peer_xor), yr, nullptr, nloc_rows >> ps.T);
+        launch_pass(ps, source(ps.peer_xor), yr, nullptr, nloc_rows >> ps.T);
         ++launches;
       }
       for (const Direct &d : plan.directs) {
@@ -1453,11 +1394,7 @@ void tiled_mult(dnm_mat_s *A, dnm_vec_t xv, dnm_vec_t yv)
     if (overlap && ps.peer_xor != 0) continue;
     const cplx *x = source(ps.peer_xor);
     const double *diag = (first && plan.use_diag) ? A->d_diag : nullptr;
-    if (u.fused) {
-      launch_fused(u, ps.T, ps.R, x, y, plan.use_diag ? A->d_diag : nullptr);
-    } else {
-      launch_pass(ps, x, y, diag, nloc_rows >> ps.T);
-    }
+    launch_pass(ps, x, y, diag, nloc_rows >> ps.T);
     first = false;
     ++launches;
   }

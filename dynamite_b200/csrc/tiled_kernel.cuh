@@ -73,7 +73,7 @@ struct PassParams {
   // the same deposit as runs of consecutive positions: outer = OR_j (tile_id & seg_mask[j]) << seg_shift[j]
   // (n_seg < 0: too many runs, use outer_pos bit by bit)
   int n_seg;
-  unsigned char seg_shift[MAX_SEGS];
+  signed char seg_shift[MAX_SEGS];  // negative: shift right (far positions above lower outer ones)
   unsigned long long seg_mask[MAX_SEGS];
   // every group is a PATH_PAIR group at t0 = 2g with row patterns of at most 8 bits: the kernels
   // run the lean group loop on SmallTables::gd
@@ -83,7 +83,8 @@ struct PassParams {
   int n_rseg;
   unsigned char rseg_shift[MAX_SEGS];
   unsigned int rseg_mask[MAX_SEGS];
-  int debug;  // timing experiments only (DNM_RING_DEBUG): bit 0 skip the arithmetic, bit 1 skip the x fetches, bit 2 skip old y
+  int far_bits;  // lowest tile-number bits = the pass's L2 window (FAR groups flip only those outer positions)
+  int debug;     // timing experiments only (DNM_TILE_DEBUG)
 };
 
 // the same tables by value, for small passes (terms indices fit u8)
@@ -100,7 +101,12 @@ struct SmallTables {
   //   x = lam, y = window bits of s1, z = window bits of s1^s2, w = pat(s1) | pat(s1^s2) << 8 | imag << 16
   // x bit 31: the next group is the imaginary group of the same mask and neither has a row
   // pattern -- the two share one gather (X and Y fields, hopping with complex amplitudes)
+  // w bit 17: FAR group -- the mask also flips index bits outside the window (inside the pass's
+  // "L2 window", PassParams::far_bits); far[g] is the whole local flip mask in index coordinates
+  // and the operand is read from global memory (an L2 hit: the tiles of one far-bit block run
+  // concurrently), not from the tile
   uint4 gd[SMALL_GROUPS];
+  unsigned long long far[SMALL_GROUPS];
 };
 
 constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v / 2); }
@@ -149,13 +155,13 @@ __device__ __forceinline__ void cp_async_wait()
 // is no per-row address arithmetic.  RING (ring kernel): rows live in pairs (quarters of the
 // tile) at element offsets qoff[0..R/2) of the ring buffer.
 // one gather serving a real and an imaginary group of the same mask: acc += (cr + i*ci) * x
-template <int R, int LOG_NT, int HI, bool RING>
-__device__ __forceinline__ void gather_fixed_cplx(double (&ar)[R], double (&ai)[R], const double2 *col, const int *qoff,
+template <int R, int LOG_NT, int HI>
+__device__ __forceinline__ void gather_fixed_cplx(double (&ar)[R], double (&ai)[R], const double2 *col,
                                                   double cr, double ci)
 {
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const double2 v = RING ? col[qoff[(r ^ HI) >> 1] + (((r ^ HI) & 1) << LOG_NT)] : col[(r ^ HI) << LOG_NT];
+    const double2 v = col[(r ^ HI) << LOG_NT];
     ar[r] += cr * v.x;
     ar[r] -= ci * v.y;
     ai[r] += cr * v.y;
@@ -163,13 +169,12 @@ __device__ __forceinline__ void gather_fixed_cplx(double (&ar)[R], double (&ai)[
   }
 }
 
-template <int R, int LOG_NT, bool RING>
-__device__ __forceinline__ void gather_switch_cplx(double (&ar)[R], double (&ai)[R], const double2 *col,
-                                                   const int *qoff, int hi_l, double cr, double ci)
+template <int R, int LOG_NT>
+__device__ __forceinline__ void gather_switch_cplx(double (&ar)[R], double (&ai)[R], const double2 *col, int hi_l, double cr, double ci)
 {
 #define DNM_HI_CASE(H) \
   case H:               \
-    if (H < R) gather_fixed_cplx<R, LOG_NT, (H < R ? H : 0), RING>(ar, ai, col, qoff, cr, ci); \
+    if (H < R) gather_fixed_cplx<R, LOG_NT, (H < R ? H : 0)>(ar, ai, col, cr, ci); \
     break;
   switch (hi_l) {
     DNM_HI_CASE(0) DNM_HI_CASE(1) DNM_HI_CASE(2) DNM_HI_CASE(3) DNM_HI_CASE(4) DNM_HI_CASE(5) DNM_HI_CASE(6)
@@ -180,14 +185,14 @@ __device__ __forceinline__ void gather_switch_cplx(double (&ar)[R], double (&ai)
 }
 
 // acc[r] += tab[q ^ rowbits(r)] * x(row r ^ HI): per-row complex coefficients read from a table
-template <int R, int LOG_NT, int HI, bool RING>
-__device__ __forceinline__ void gather_fixed_ctab(double (&ar)[R], double (&ai)[R], const double2 *col, const int *qoff,
+template <int R, int LOG_NT, int HI>
+__device__ __forceinline__ void gather_fixed_ctab(double (&ar)[R], double (&ai)[R], const double2 *col,
                                                   const double2 *tab, u32 q, unsigned long long rp)
 {
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const double2 c = __ldg(&tab[q ^ (u32)((rp >> (8 * (r & 7))) & 0xffull)]);
-    const double2 v = RING ? col[qoff[(r ^ HI) >> 1] + (((r ^ HI) & 1) << LOG_NT)] : col[(r ^ HI) << LOG_NT];
+    const double2 v = col[(r ^ HI) << LOG_NT];
     ar[r] += c.x * v.x;
     ar[r] -= c.y * v.y;
     ai[r] += c.x * v.y;
@@ -195,14 +200,13 @@ __device__ __forceinline__ void gather_fixed_ctab(double (&ar)[R], double (&ai)[
   }
 }
 
-template <int R, int LOG_NT, bool RING>
-__device__ __forceinline__ void gather_switch_ctab(double (&ar)[R], double (&ai)[R], const double2 *col,
-                                                   const int *qoff, int hi_l, const double2 *tab, u32 q,
+template <int R, int LOG_NT>
+__device__ __forceinline__ void gather_switch_ctab(double (&ar)[R], double (&ai)[R], const double2 *col, int hi_l, const double2 *tab, u32 q,
                                                    unsigned long long rp)
 {
 #define DNM_HI_CASE(H) \
   case H:               \
-    if (H < R) gather_fixed_ctab<R, LOG_NT, (H < R ? H : 0), RING>(ar, ai, col, qoff, tab, q, rp); \
+    if (H < R) gather_fixed_ctab<R, LOG_NT, (H < R ? H : 0)>(ar, ai, col, tab, q, rp); \
     break;
   switch (hi_l) {
     DNM_HI_CASE(0) DNM_HI_CASE(1) DNM_HI_CASE(2) DNM_HI_CASE(3) DNM_HI_CASE(4) DNM_HI_CASE(5) DNM_HI_CASE(6)
@@ -212,8 +216,8 @@ __device__ __forceinline__ void gather_switch_ctab(double (&ar)[R], double (&ai)
 #undef DNM_HI_CASE
 }
 
-template <int R, int LOG_NT, int HI, bool IMAG, bool SCALAR, bool RING>
-__device__ __forceinline__ void gather_fixed(double (&ar)[R], double (&ai)[R], const double2 *col, const int *qoff,
+template <int R, int LOG_NT, int HI, bool IMAG, bool SCALAR>
+__device__ __forceinline__ void gather_fixed(double (&ar)[R], double (&ai)[R], const double2 *col,
                                              double d0, const double (&d)[R])
 {
 #pragma unroll
@@ -222,7 +226,7 @@ __device__ __forceinline__ void gather_fixed(double (&ar)[R], double (&ai)[R], c
     // rows with a zero coefficient (flip-flop terms: half of them) are not fetched; shared-memory
     // bandwidth is what bounds the arithmetic phase
     if (!SCALAR && c == 0.0) continue;
-    const double2 v = RING ? col[qoff[(r ^ HI) >> 1] + (((r ^ HI) & 1) << LOG_NT)] : col[(r ^ HI) << LOG_NT];
+    const double2 v = col[(r ^ HI) << LOG_NT];
     if (IMAG) {
       ar[r] -= c * v.y;
       ai[r] += c * v.x;
@@ -233,13 +237,13 @@ __device__ __forceinline__ void gather_fixed(double (&ar)[R], double (&ai)[R], c
   }
 }
 
-template <int R, int LOG_NT, bool IMAG, bool SCALAR, bool RING>
-__device__ __forceinline__ void gather_switch(double (&ar)[R], double (&ai)[R], const double2 *col, const int *qoff,
+template <int R, int LOG_NT, bool IMAG, bool SCALAR>
+__device__ __forceinline__ void gather_switch(double (&ar)[R], double (&ai)[R], const double2 *col,
                                               int hi_l, double d0, const double (&d)[R])
 {
 #define DNM_HI_CASE(H) \
   case H:               \
-    if (H < R) gather_fixed<R, LOG_NT, (H < R ? H : 0), IMAG, SCALAR, RING>(ar, ai, col, qoff, d0, d); \
+    if (H < R) gather_fixed<R, LOG_NT, (H < R ? H : 0), IMAG, SCALAR>(ar, ai, col, d0, d); \
     break;
   switch (hi_l) {
     DNM_HI_CASE(0) DNM_HI_CASE(1) DNM_HI_CASE(2) DNM_HI_CASE(3) DNM_HI_CASE(4) DNM_HI_CASE(5) DNM_HI_CASE(6)
@@ -256,7 +260,11 @@ __device__ __forceinline__ i64 tile_outer_bits(const PassParams &P, unsigned lon
 {
   i64 g = 0;
   if (P.n_seg >= 0) {
-    for (int j = 0; j < P.n_seg; ++j) g |= (i64)((tile_id & P.seg_mask[j]) << P.seg_shift[j]);
+    for (int j = 0; j < P.n_seg; ++j) {
+      const unsigned long long v = tile_id & P.seg_mask[j];
+      const int sh = P.seg_shift[j];
+      g |= (i64)(sh >= 0 ? (v << sh) : (v >> (-sh)));
+    }
   } else {
     for (int k = 0; k < P.n_outer; ++k) g |= (i64)((tile_id >> k) & 1ull) << P.outer_pos[k];
   }
@@ -329,14 +337,51 @@ __device__ __forceinline__ void stage_tile(const PassParams &P, const SmallTable
   __syncthreads();
 }
 
+// acc[r] += (IMAG ? i*d_r : d_r) * x[row r ^ m] for a FAR mask m: coalesced 16-byte loads from
+// global memory (L2), four rows in flight at a time
+__device__ __forceinline__ double2 ld_far(const cplx *p)
+{
+  double2 v;
+  asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+template <int R, bool SCALAR>
+__device__ __forceinline__ void gather_far(double (&ar)[R], double (&ai)[R], const cplx *__restrict__ xg, i64 base_g,
+                                           const PassParams &P, i64 m, bool imag, double d0, const double (&d)[R])
+{
+  constexpr int CH = R < 4 ? R : 4;
+#pragma unroll
+  for (int h = 0; h < R; h += CH) {
+    double2 v[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const double c = SCALAR ? d0 : d[h + k];
+      v[k] = make_double2(0.0, 0.0);
+      if (SCALAR || c != 0.0) v[k] = ld_far(xg + ((base_g | P.roff[h + k]) ^ m));
+    }
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const double c = SCALAR ? d0 : d[h + k];
+      if (imag) {
+        ar[h + k] -= c * v[k].y;
+        ai[h + k] += c * v[k].x;
+      } else {
+        ar[h + k] += c * v[k].x;
+        ai[h + k] += c * v[k].y;
+      }
+    }
+  }
+}
+
 // The lean group loop (P.lean): every group has at most two distinct sign masks, so
 //   D(l) = sigma(s1 & l) * (c1 + c2 * sigma((s1^s2) & l))
 // and a group costs one 16-byte descriptor (kernel-parameter memory, uniform), one 16-byte
 // scratch read (c1+c2, c1-c2 with the tile signs folded in), two popcounts and the gather.
-template <int R, int LOG_NT, bool RING>
+template <int R, int LOG_NT>
 __device__ __forceinline__ void process_groups_lean(const PassParams &P, const SmallTables &S, const double2 *tile,
                                                     const double *csign, double (&ar)[R], double (&ai)[R],
-                                                    const int *qoff)
+                                                    const cplx *__restrict__ xg, i64 base_g)
 {
   constexpr int NT = 1 << LOG_NT;
   const int tid = threadIdx.x;
@@ -348,9 +393,15 @@ __device__ __forceinline__ void process_groups_lean(const PassParams &P, const S
     const double2 *col = tile + (tid ^ (int)(gd.x & (NT - 1)));
     const int hi = (int)((gd.x & 0x7fffffffu) >> LOG_NT);
     const int pa = __popc(gd.y & (u32)tid) & 1, pb = __popc(gd.z & (u32)tid) & 1;
-    const bool imag = (gd.w >> 16) != 0;
+    const bool imag = ((gd.w >> 16) & 1u) != 0;
+    const bool far = ((gd.w >> 17) & 1u) != 0;
     if ((gd.w & 0xffffu) == 0) {
       const double c = flip_sign(pb ? cc.y : cc.x, pa);
+      if (far) {
+        const double none[R] = {};
+        if (c != 0.0) gather_far<R, true>(ar, ai, xg, base_g, P, (i64)S.far[g], imag, c, none);
+        continue;
+      }
       if (gd.x >> 31) {
         // real and imaginary group of one mask: one fetch, a complex coefficient
         ++g;
@@ -358,13 +409,13 @@ __device__ __forceinline__ void process_groups_lean(const PassParams &P, const S
         const double2 ci2 = cpm[g];
         const int qa = __popc(gi.y & (u32)tid) & 1, qb = __popc(gi.z & (u32)tid) & 1;
         const double ci = flip_sign(qb ? ci2.y : ci2.x, qa);
-        if (c != 0.0 || ci != 0.0) gather_switch_cplx<R, LOG_NT, RING>(ar, ai, col, qoff, hi, c, ci);
+        if (c != 0.0 || ci != 0.0) gather_switch_cplx<R, LOG_NT>(ar, ai, col, hi, c, ci);
         continue;
       }
       if (c != 0.0) {
         const double none[R] = {};
-        if (imag) gather_switch<R, LOG_NT, true, true, RING>(ar, ai, col, qoff, hi, c, none);
-        else gather_switch<R, LOG_NT, false, true, RING>(ar, ai, col, qoff, hi, c, none);
+        if (imag) gather_switch<R, LOG_NT, true, true>(ar, ai, col, hi, c, none);
+        else gather_switch<R, LOG_NT, false, true>(ar, ai, col, hi, c, none);
       }
     } else {
       const u32 qa = (gd.w & 0xffu) ^ (0u - (u32)pa), qb = ((gd.w >> 8) & 0xffu) ^ (0u - (u32)pb);
@@ -376,9 +427,11 @@ __device__ __forceinline__ void process_groups_lean(const PassParams &P, const S
         d[r] = flip_if(__double2hiint(c), __double2loint(c), qa, r);
         any = any || (c != 0.0);
       }
-      if (any) {
-        if (imag) gather_switch<R, LOG_NT, true, false, RING>(ar, ai, col, qoff, hi, 0.0, d);
-        else gather_switch<R, LOG_NT, false, false, RING>(ar, ai, col, qoff, hi, 0.0, d);
+      if (any && far) {
+        gather_far<R, false>(ar, ai, xg, base_g, P, (i64)S.far[g], imag, 0.0, d);
+      } else if (any) {
+        if (imag) gather_switch<R, LOG_NT, true, false>(ar, ai, col, hi, 0.0, d);
+        else gather_switch<R, LOG_NT, false, false>(ar, ai, col, hi, 0.0, d);
       }
     }
   }
@@ -387,12 +440,12 @@ __device__ __forceinline__ void process_groups_lean(const PassParams &P, const S
 // Accumulate every group of the pass into this thread's R rows  l = tid + r*NT.
 // Contiguous tile: `tile` is the 2^T-entry buffer.  RING mode (ring kernel): the tile is four
 // quarters (row pairs) at element offsets qoff[0..3] of `tile`.
-template <int R, int LOG_NT, bool SMALL, bool RING = false>
+template <int R, int LOG_NT, bool SMALL>
 __device__ __forceinline__ void process_groups(const PassParams &P, const SmallTables &S, const double2 *tile,
                                                const double *csign, i64 outer_g, double (&ar)[R], double (&ai)[R],
-                                               const int *qoff = nullptr)
+                                               const cplx *__restrict__ xg, i64 base_g)
 {
-  if (SMALL && R <= 8 && P.lean) return process_groups_lean<R, LOG_NT, RING>(P, S, tile, csign, ar, ai, qoff);
+  if (SMALL && R <= 8 && P.lean) return process_groups_lean<R, LOG_NT>(P, S, tile, csign, ar, ai, xg, base_g);
   constexpr int NT = 1 << LOG_NT;
   constexpr int rbase = 0;
   constexpr int RH = R;
@@ -440,8 +493,8 @@ __device__ __forceinline__ void process_groups(const PassParams &P, const SmallT
         const double c = flip_sign(pb ? cc.y : cc.x, pa);
         if (c != 0.0) {
           const double none[RH] = {};
-          if (imag) gather_switch<RH, LOG_NT, true, true, RING>(ar, ai, col, qoff, hi_lo, c, none);
-          else gather_switch<RH, LOG_NT, false, true, RING>(ar, ai, col, qoff, hi_lo, c, none);
+          if (imag) gather_switch<RH, LOG_NT, true, true>(ar, ai, col, hi_lo, c, none);
+          else gather_switch<RH, LOG_NT, false, true>(ar, ai, col, hi_lo, c, none);
         }
       } else {
         const u32 qa = pata ^ (0u - (u32)pa), qb = patb ^ (0u - (u32)pb);
@@ -454,8 +507,8 @@ __device__ __forceinline__ void process_groups(const PassParams &P, const SmallT
           any = any || (c != 0.0);
         }
         if (any) {
-          if (imag) gather_switch<RH, LOG_NT, true, false, RING>(ar, ai, col, qoff, hi_lo, 0.0, d);
-          else gather_switch<RH, LOG_NT, false, false, RING>(ar, ai, col, qoff, hi_lo, 0.0, d);
+          if (imag) gather_switch<RH, LOG_NT, true, false>(ar, ai, col, hi_lo, 0.0, d);
+          else gather_switch<RH, LOG_NT, false, false>(ar, ai, col, hi_lo, 0.0, d);
         }
       }
       continue;
@@ -473,7 +526,7 @@ __device__ __forceinline__ void process_groups(const PassParams &P, const SmallT
         q |= (p & 1u) << (t - t0);
       }
       const double2 *tab = reinterpret_cast<const double2 *>(P.tabs + __ldg(&P.toff[g]));
-      gather_switch_ctab<R, LOG_NT, RING>(ar, ai, col, qoff, hi_lo, tab, q, __ldg(&P.rpat[g]));
+      gather_switch_ctab<R, LOG_NT>(ar, ai, col, hi_lo, tab, q, __ldg(&P.rpat[g]));
       continue;
     }
     double c0 = 0.0;  // terms without r bits: one scalar per thread
@@ -483,8 +536,8 @@ __device__ __forceinline__ void process_groups(const PassParams &P, const SmallT
     if (path == PATH_SCALAR) {
       if (c0 != 0.0) {
         const double none[RH] = {};
-        if (imag) gather_switch<RH, LOG_NT, true, true, RING>(ar, ai, col, qoff, hi_lo, c0, none);
-        else gather_switch<RH, LOG_NT, false, true, RING>(ar, ai, col, qoff, hi_lo, c0, none);
+        if (imag) gather_switch<RH, LOG_NT, true, true>(ar, ai, col, hi_lo, c0, none);
+        else gather_switch<RH, LOG_NT, false, true>(ar, ai, col, hi_lo, c0, none);
       }
     } else {
       double d[RH];
@@ -557,8 +610,8 @@ __device__ __forceinline__ void process_groups(const PassParams &P, const SmallT
         for (int r = 0; r < RH; ++r) any = any || (d[r] != 0.0);
       }
       if (any) {
-        if (imag) gather_switch<RH, LOG_NT, true, false, RING>(ar, ai, col, qoff, hi_lo, 0.0, d);
-        else gather_switch<RH, LOG_NT, false, false, RING>(ar, ai, col, qoff, hi_lo, 0.0, d);
+        if (imag) gather_switch<RH, LOG_NT, true, false>(ar, ai, col, hi_lo, 0.0, d);
+        else gather_switch<RH, LOG_NT, false, false>(ar, ai, col, hi_lo, 0.0, d);
       }
     }
   }
@@ -590,7 +643,7 @@ __device__ __forceinline__ void tile_body(const PassParams &P, const SmallTables
     for (int r = 0; r < R; ++r) ar[r] = ai[r] = 0.0;
   }
 
-  process_groups<R, LOG_NT, SMALL>(P, S, tile, csign, outer_g, ar, ai);
+  process_groups<R, LOG_NT, SMALL>(P, S, tile, csign, outer_g, ar, ai, x, base_g);
 
   if (P.accumulate == 2) {
     // passes of a small problem run concurrently in one grid: combine in the L2 with FP64 atomics
@@ -631,146 +684,6 @@ __global__ void __launch_bounds__(TileCfg<T, R>::NT, TileCfg<T, R>::MINB)
   tile_body<T, R, SMALL>(P, S, outer, thread_base(P, outer), x, y, diag, tile, csign);
 }
 
-// ---- pipelined persistent kernel ----------------------------------------------------------
-// k_tiled serialises, inside a CTA, "fetch the tile -> arithmetic -> fetch old y -> store"; the
-// memory system only stays busy because other CTAs of the SM are in a different phase, and a
-// 128 KiB tile (T=13, the size that needs the fewest sweeps over HBM) leaves room for one CTA
-// only.  Here a persistent CTA walks tiles handed out by a ticket counter and keeps SEVEN
-// quarter-tile buffers (a quarter = the two rows 2q, 2q+1 of every thread): four hold the tile
-// being evaluated, the other three receive quarters 0..2 of the NEXT tile (cp.async) while the
-// arithmetic runs.  After the arithmetic the last quarter of the next tile goes into a buffer
-// the finished tile frees, together with the old y of the finished tile (read-modify-write
-// passes; six rows through the freed buffers, two through registers) -- one exposed round trip
-// per tile instead of two plus a whole tile fetch.
-template <int T>
-struct RingCfg {
-  static constexpr int R = 8;
-  static constexpr int NT = 1 << (T - 3);
-  static constexpr int LOG_NT = T - 3;
-  static constexpr int QUARTER = 1 << (T - 2);  // amplitudes per quarter tile
-  static constexpr int SLOTS = 7;
-  static constexpr size_t RING_BYTES = (size_t)SLOTS * QUARTER * sizeof(double2);
-  // resident CTAs per SM: 1024 threads of 64 registers, and 228 KiB of shared memory
-  static constexpr int BY_REGS = 65536 / (NT * 64) < 1 ? 1 : 65536 / (NT * 64);
-  static constexpr int BY_SMEM = (int)(233472 / (RING_BYTES + 2048));
-  static constexpr int CTAS = BY_REGS < BY_SMEM ? BY_REGS : BY_SMEM;
-};
-
-template <int T, bool SMALL>
-__global__ void __launch_bounds__(RingCfg<T>::NT, RingCfg<T>::CTAS)
-    k_tiled_ring(const __grid_constant__ PassParams P, const __grid_constant__ SmallTables S,
-                 const cplx *__restrict__ x, cplx *__restrict__ y, const double *__restrict__ diag,
-                 unsigned long long ntiles, unsigned long long *ticket)
-{
-  typedef RingCfg<T> C;
-  constexpr int NT = C::NT, LOG_NT = C::LOG_NT, R = C::R, Q = C::QUARTER;
-  extern __shared__ double2 ring[];
-  __shared__ __align__(16) double csign_small[SMALL ? SMALL_TERMS : 2];
-  __shared__ unsigned long long s_tile;
-  double *csign = SMALL ? csign_small : reinterpret_cast<double *>(ring + C::SLOTS * Q);
-  const int tid = threadIdx.x;
-  const i64 tbase = __ldg(&P.rowoff[tid >> P.B]) | (i64)(tid & ((1 << P.B) - 1));
-  const bool rmw = P.accumulate == 1;
-
-  // element offsets of the buffers: cur[q] holds quarter q of the tile being evaluated, nxt[q]
-  // receives quarter q (< 3) of the next one
-  int cur[4] = {0, Q, 2 * Q, 3 * Q};
-  int nxt[3] = {4 * Q, 5 * Q, 6 * Q};
-
-  if (tid == 0) s_tile = atomicAdd(ticket, 1ull);
-  __syncthreads();
-  unsigned long long tile_id = s_tile;
-  __syncthreads();  // s_tile is rewritten at the top of the loop
-  i64 outer = 0, base_g = 0;
-  double dg[R];  // the diagonal of the tile about to be evaluated (writing pass)
-  if (tile_id < ntiles) {
-    outer = tile_outer_bits(P, tile_id);
-    base_g = outer | tbase;
-#pragma unroll
-    for (int r = 0; r < R; ++r) cp_async16(&ring[cur[r >> 1] + (r & 1) * NT + tid], &x[base_g | P.roff[r]]);
-    if (diag != nullptr) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) dg[r] = __ldg(&diag[base_g | P.roff[r]]);
-    }
-  }
-  cp_async_commit();
-
-#pragma unroll 1
-  while (tile_id < ntiles) {
-    const i64 outer_g = outer | P.rank_bits;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1ull);  // the tile after this one
-    stage_tables<NT, SMALL>(P, S, outer_g, csign);
-    cp_async_wait<0>();
-    __syncthreads();  // the whole tile (and its scratch, and s_tile) is visible
-    const unsigned long long next_id = s_tile;
-    i64 outer_n = 0, base_n = 0;
-    if (next_id < ntiles) {
-      outer_n = tile_outer_bits(P, next_id);
-      base_n = outer_n | tbase;
-      if (!(P.debug & 2))
-#pragma unroll
-      for (int r = 0; r < 6; ++r) cp_async16(&ring[nxt[r >> 1] + (r & 1) * NT + tid], &x[base_n | P.roff[r]]);
-    }
-    cp_async_commit();
-
-    double ar[R], ai[R];
-    if (diag != nullptr) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const double2 v = ring[cur[r >> 1] + (r & 1) * NT + tid];
-        ar[r] = dg[r] * v.x;
-        ai[r] = dg[r] * v.y;
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < R; ++r) ar[r] = ai[r] = 0.0;
-    }
-    if (!(P.debug & 1)) process_groups<R, LOG_NT, SMALL, true>(P, S, ring, csign, outer_g, ar, ai, cur);
-
-    __syncthreads();  // nobody reads this tile (or its scratch) any more
-    if (next_id < ntiles && !(P.debug & 2)) {
-#pragma unroll
-      for (int r = 6; r < R; ++r) cp_async16(&ring[cur[0] + (r & 1) * NT + tid], &x[base_n | P.roff[r]]);
-    }
-    if (rmw && !(P.debug & 4)) {
-      // old y: rows 0..5 through the three buffers this tile frees (each thread reads back only
-      // what it copied itself), rows 6 and 7 through registers
-#pragma unroll
-      for (int r = 0; r < 6; ++r) cp_async16(&ring[cur[1 + (r >> 1)] + (r & 1) * NT + tid], &y[base_g | P.roff[r]]);
-      const double2 o6 = y[base_g | P.roff[6]], o7 = y[base_g | P.roff[7]];
-      cp_async_commit();
-      cp_async_wait<0>();
-#pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        const double2 old = ring[cur[1 + (r >> 1)] + (r & 1) * NT + tid];
-        y[base_g | P.roff[r]] = make_double2(ar[r] + old.x, ai[r] + old.y);
-      }
-      y[base_g | P.roff[6]] = make_double2(ar[6] + o6.x, ai[6] + o6.y);
-      y[base_g | P.roff[7]] = make_double2(ar[7] + o7.x, ai[7] + o7.y);
-    } else {
-      cp_async_commit();
-#pragma unroll
-      for (int r = 0; r < R; ++r) y[base_g | P.roff[r]] = make_double2(ar[r], ai[r]);
-    }
-    if (diag != nullptr && next_id < ntiles) {  // in flight together with the last quarter
-#pragma unroll
-      for (int r = 0; r < R; ++r) dg[r] = __ldg(&diag[base_n | P.roff[r]]);
-    }
-    // rotate the buffers
-    const int c0 = cur[0], c1 = cur[1], c2 = cur[2], c3 = cur[3];
-    cur[0] = nxt[0];
-    cur[1] = nxt[1];
-    cur[2] = nxt[2];
-    cur[3] = c0;
-    nxt[0] = c1;
-    nxt[1] = c2;
-    nxt[2] = c3;
-    tile_id = next_id;
-    outer = outer_n;
-    base_g = base_n;
-  }
-}
-
 // every pass of a small problem in ONE launch (blockIdx.y = pass): a pass of an L2-resident vector
 // has too few tiles to fill the GPU, and the passes only interact through y, which is combined
 // with atomics.  Tables come from global memory (PassParams array on the device).
@@ -786,101 +699,6 @@ __global__ void __launch_bounds__(TileCfg<T, R>::NT, TileCfg<T, R>::MINB)
   const i64 outer = tile_outer_bits(P, blockIdx.x);
   tile_body<T, R, false>(P, unused, outer, thread_base(P, outer), x, y, ((int)blockIdx.y == diag_pass) ? diag : nullptr,
                          tile, csign);
-}
-
-// ---- L2-fused passes ---------------------------------------------------------------------
-// Consecutive passes whose windows together span only u index bits work on CHUNKS of 2^u
-// amplitudes (all indices that agree outside those u bits).  If pass k+1 of a chunk runs soon
-// after pass k of the same chunk, its x tile and the y it read-modify-writes are still in the
-// 126 MB L2, so the pair costs one x read and one y write of DRAM traffic instead of two reads,
-// a y re-read and two writes.  One persistent kernel walks the (chunk, pass, tile) items in an
-// order where pass k of chunk c is issued `lag` chunks after pass k-1 of chunk c; a CTA takes
-// the next item with an atomic ticket, waits on a per-(pass, chunk) completion counter when
-// the item is not the first pass, and bumps the counter when it is done.  Tickets are handed
-// out in dependency order, so the scheme cannot deadlock whatever the residency.
-constexpr int MAX_FUSED_PASSES = 4;
-
-struct FusedParams {
-  PassParams p[MAX_FUSED_PASSES];
-  SmallTables s[MAX_FUSED_PASSES];
-  int npasses;
-  int lag;                 // chunks between consecutive passes of the same chunk
-  int log_tiles;           // log2(tiles per chunk per pass)
-  long long nchunks;
-  unsigned long long nitems;
-  int *done;               // [(npasses-1) * nchunks] tiles finished per (pass, chunk)
-  unsigned long long *ticket;
-  int diag_pass;           // pass that applies the cached diagonal (-1: none)
-  int prefetch;            // warm the L2 with the next tile (local x only: peer memory bypasses the L2)
-};
-
-template <int T, int R>
-__global__ void __launch_bounds__(TileCfg<T, R>::NT, TileCfg<T, R>::MINB)
-    k_tiled_fused(const __grid_constant__ FusedParams F, const cplx *__restrict__ x, cplx *__restrict__ y,
-                  const double *__restrict__ diag)
-{
-  extern __shared__ double2 tile[];
-  __shared__ __align__(16) double csign[SMALL_TERMS];
-  __shared__ unsigned long long s_item;
-  const int tiles = 1 << F.log_tiles;
-  const unsigned long long per_step = (unsigned long long)F.npasses * tiles;
-
-  // decode an item; returns false for the ramp-up / ramp-down slots and past the end
-  auto decode = [&](unsigned long long item, int &k, long long &c, unsigned long long &tile_id) -> bool {
-    if (item >= F.nitems) return false;
-    const long long step = (long long)(item / per_step);
-    const int rem = (int)(item % per_step);
-    k = rem >> F.log_tiles;
-    c = step - (long long)k * F.lag;
-    tile_id = (unsigned long long)(rem & (tiles - 1)) | ((unsigned long long)c << F.log_tiles);
-    return c >= 0 && c < F.nchunks;
-  };
-
-  if (threadIdx.x == 0) s_item = atomicAdd(F.ticket, 1ull);
-  __syncthreads();
-  unsigned long long item = s_item;
-  while (item < F.nitems) {
-    __syncthreads();  // everyone has read s_item; the previous item's smem reads are finished
-    if (threadIdx.x == 0) s_item = atomicAdd(F.ticket, 1ull);  // the item after this one
-    int k;
-    long long c;
-    unsigned long long tile_id;
-    const bool live = decode(item, k, c, tile_id);
-    if (live) {
-      const PassParams &P = F.p[k];
-      const i64 outer = tile_outer_bits(P, tile_id);
-      const i64 base_g = thread_base(P, outer);
-      // the old y of this tile is needed only at the end: start pulling it into the L2 now
-      if (P.accumulate && F.prefetch) prefetch_tile_l2<R>(P, y, base_g);
-      if (k > 0) {
-        if (threadIdx.x == 0) {
-          const volatile int *flag = F.done + (size_t)(k - 1) * F.nchunks + c;
-          while (*flag < tiles) __nanosleep(64);
-          __threadfence();
-        }
-      }
-      __syncthreads();  // dependency satisfied; s_item (next) is published
-      {
-        // warm the L2 with the next item's x tile while this one is being computed
-        int kn;
-        long long cn;
-        unsigned long long tn;
-        if (F.prefetch && decode(s_item, kn, cn, tn)) {
-          const PassParams &Pn = F.p[kn];
-          prefetch_tile_l2<R>(Pn, x, thread_base(Pn, tile_outer_bits(Pn, tn)));
-        }
-      }
-      tile_body<T, R, true>(P, F.s[k], outer, base_g, x, y, (k == F.diag_pass) ? diag : nullptr, tile, csign);
-      if (k + 1 < F.npasses) {
-        __threadfence();  // this thread's y stores are visible device-wide
-        __syncthreads();
-        if (threadIdx.x == 0) atomicAdd(F.done + (size_t)k * F.nchunks + c, 1);
-      }
-    } else {
-      __syncthreads();
-    }
-    item = s_item;
-  }
 }
 
 }  // namespace tiled

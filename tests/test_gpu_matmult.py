@@ -55,9 +55,10 @@ def test_tiled_kernel_vs_oracle(gpu, tag, L, tile_bits):
             mat.set_option('tile_rows', 16)      # 16 rows per thread
             assert rel_err(device_mult(mat, x), want) < TOL, (tag, L, tile_bits, diag, 'rows=16')
             mat.set_option('tile_rows', 0)
-            mat.set_option('pipeline', 1)        # the persistent ring kernel instead of one tile per CTA
-            assert rel_err(device_mult(mat, x), want) < TOL, (tag, L, tile_bits, diag, 'ring kernel')
-            mat.set_option('pipeline', 0)
+        for far in (1, 3):                       # masks that leave the window served through the L2 window
+            mat.set_option('far_bits', far)
+            assert rel_err(device_mult(mat, x), want) < TOL, (tag, L, tile_bits, diag, 'far_bits', far)
+        mat.set_option('far_bits', 0)
         mat.set_option('kernel', 1)
         y1 = device_mult(mat, x)
         assert mat.get_info('kernel') == 1
@@ -65,30 +66,52 @@ def test_tiled_kernel_vs_oracle(gpu, tag, L, tile_bits):
         mat.destroy()
 
 
-@pytest.mark.parametrize('name,L', [('MBL', 20), ('SYK', 15), ('long_range', 18)])
-def test_pipelined_kernel_many_tiles_per_cta(gpu, name, L, monkeypatch):
-    """Every persistent CTA of k_tiled_ring walks many tiles (buffer rotation, prefetch, ticket
-    hand-out): the grid is capped to a few CTAs.  Checked against the oracle's fast path, as is the
-    one-tile-per-CTA kernel."""
+@pytest.mark.parametrize('name,L', [('MBL', 20), ('heisenberg', 19), ('long_range', 18), ('ising', 18), ('XX', 19)])
+def test_far_masks_l2_window(gpu, name, L):
+    """FAR masks: a pass serves masks that leave its shared-memory window from global memory (the
+    L2 window = the lowest tile-number bits).  Every (tile size, far_bits) combination changes which
+    masks are far and the tile order; all are checked against the oracle's fast path."""
     from dynamite_b200.hamiltonians import build_hamiltonian
     H = build_hamiltonian(name, L)
     H.reduce_msc()
     terms = [(int(m), int(s), complex(c)) for m, s, c in zip(H.msc['masks'], H.msc['signs'], H.msc['coeffs'])]
-    spec = {'type': 'parity', 'L': L, 'space': 0} if name == 'SYK' else {'type': 'full', 'L': L}
+    spec = {'type': 'full', 'L': L}
     sub = oracle.Subspace(spec)
     x = rand_state(sub.dim, 5)
     want, _ = oracle.matmult_fast(oracle.Msc.from_terms(terms), sub, x, nthreads=8)
     for diag in (True, False):
         mat = product_mat(terms, spec, spec, False, precompute_diag=diag)
         mat.set_option('kernel', 2)
-        for tile_bits in (10, 11, 12, 13):
+        base = None
+        for tile_bits in (9, 10, 11, 12, 13):
             mat.set_option('tile_bits', tile_bits)
-            for cap in ('3', '7', ''):
-                monkeypatch.setenv('DNM_PIPE_CTAS', cap)
-                mat.set_option('pipeline', 1)
-                assert rel_err(device_mult(mat, x), want) < TOL, (name, tile_bits, diag, cap, 'pipelined')
-            mat.set_option('pipeline', 2)
-            assert rel_err(device_mult(mat, x), want) < TOL, (name, tile_bits, diag, 'one tile per CTA')
+            for far in (0, 2, 5, 8, 12):
+                mat.set_option('far_bits', far)
+                assert rel_err(device_mult(mat, x), want) < TOL, (name, tile_bits, diag, far)
+                if far == 0:
+                    base = mat.get_info('passes')
+                else:
+                    assert mat.get_info('passes') <= base
+        mat.destroy()
+
+
+def test_far_masks_parity_subspace(gpu):
+    from dynamite_b200.hamiltonians import build_hamiltonian
+    L = 18
+    H = build_hamiltonian('heisenberg', L)
+    H.reduce_msc()
+    terms = [(int(m), int(s), complex(c)) for m, s, c in zip(H.msc['masks'], H.msc['signs'], H.msc['coeffs'])]
+    for space in (0, 1):
+        spec = {'type': 'parity', 'L': L, 'space': space}
+        sub = oracle.Subspace(spec)
+        x = rand_state(sub.dim, 7)
+        want, _ = oracle.matmult_fast(oracle.Msc.from_terms(terms), sub, x, nthreads=8)
+        mat = product_mat(terms, spec, spec, False, precompute_diag=True)
+        mat.set_option('kernel', 2)
+        for tile_bits, far in ((10, 4), (11, 6), (12, 3)):
+            mat.set_option('tile_bits', tile_bits)
+            mat.set_option('far_bits', far)
+            assert rel_err(device_mult(mat, x), want) < TOL, (space, tile_bits, far)
         mat.destroy()
 
 
