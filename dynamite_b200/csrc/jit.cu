@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
@@ -23,7 +24,7 @@ struct Out {
   std::string s;
   void operator()(const char *fmt, ...)
   {
-    char buf[1024];
+    char buf[2048];
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
@@ -41,7 +42,7 @@ std::string hexd(double v)
 
 int par32(u32 v) { return __builtin_parity(v); }
 
-// "(tid & m) << s | ..." for the runs of consecutive window positions W[lo..hi)
+// "(var & m) << s | ..." for the runs of consecutive window positions W[lo..hi)
 std::string deposit_expr(const char *var, const std::vector<int> &W, int lo, int hi)
 {
   std::string e;
@@ -60,6 +61,108 @@ std::string deposit_expr(const char *var, const std::vector<int> &W, int lo, int
   return e.empty() ? "(i64)0" : e;
 }
 
+// tile number -> index bits outside the window
+std::string outer_expr(const PassParams &P, const char *var)
+{
+  std::string e;
+  char buf[200];
+  if (P.n_seg >= 0) {
+    for (int j = 0; j < P.n_seg; ++j) {
+      const int sh = P.seg_shift[j];
+      snprintf(buf, sizeof(buf), "((%s & 0x%llxull) %s %d)", var, (u64)P.seg_mask[j], sh >= 0 ? "<<" : ">>", sh >= 0 ? sh : -sh);
+      if (!e.empty()) e += " | ";
+      e += buf;
+    }
+  } else {
+    for (int k = 0; k < P.n_outer; ++k) {
+      snprintf(buf, sizeof(buf), "(((%s >> %d) & 1ull) << %d)", var, k, (int)P.outer_pos[k]);
+      if (!e.empty()) e += " | ";
+      e += buf;
+    }
+  }
+  return e.empty() ? "0ull" : e;
+}
+
+// geometry of the thread <-> row mapping: thread `tid` owns the rows l = tid + r * NT
+struct Geo {
+  int T, R, LOGR, LOG_NT, NT;
+  i64 roff[8];   // index offset of row group r
+  i64 rowbits;   // index positions of the row coordinates
+  Geo(const PassDesc &pd)
+  {
+    T = pd.T;
+    R = pd.rows;
+    LOGR = (R == 8) ? 3 : 2;
+    LOG_NT = T - LOGR;
+    NT = 1 << LOG_NT;
+    rowbits = 0;
+    for (int r = 0; r < R; ++r) {
+      roff[r] = 0;
+      for (int k = 0; k < LOGR; ++k)
+        if ((r >> k) & 1) roff[r] |= (i64)1 << pd.W[LOG_NT + k];
+    }
+    for (int k = 0; k < LOGR; ++k) rowbits |= (i64)1 << pd.W[LOG_NT + k];
+  }
+};
+
+// The tile as a box of a tensor over the local index space (element = double).
+struct Box {
+  int rank = -1;  // -1: not expressible, 0: the tile is contiguous
+  u64 dims[MAX_TMA_RANK], strides[MAX_TMA_RANK];
+  u32 box[MAX_TMA_RANK];
+  int lo[MAX_TMA_RANK], len[MAX_TMA_RANK];  // bit range of the dimension
+  bool window[MAX_TMA_RANK];
+};
+
+Box tile_box(const PassDesc &pd)
+{
+  Box b;
+  const int n = pd.nloc, T = pd.T;
+  std::vector<char> inw(n, 0);
+  for (int w : pd.W) inw[w] = 1;
+  bool contiguous = true;
+  for (int j = 0; j < T; ++j) contiguous = contiguous && pd.W[j] == j;
+  if (contiguous) {
+    b.rank = 0;
+    return b;
+  }
+  if (!inw[0]) return b;
+  int rank = 0, pos = 0;
+  while (pos < n) {
+    int e = pos + 1;
+    while (e < n && inw[e] == inw[pos]) ++e;
+    if (inw[pos]) {
+      int q = pos;
+      while (q < e) {
+        const int cap = (q == 0) ? 7 : 8;  // box extents are at most 256 elements (the innermost counts doubles)
+        const int l = std::min(cap, e - q);
+        if (rank == MAX_TMA_RANK) return b;
+        b.lo[rank] = q;
+        b.len[rank] = l;
+        b.window[rank] = true;
+        b.dims[rank] = (q == 0) ? (2ull << l) : (1ull << l);
+        b.box[rank] = (u32)b.dims[rank];
+        b.strides[rank] = 16ull << q;
+        ++rank;
+        q += l;
+      }
+    } else {
+      if (rank == MAX_TMA_RANK) return b;
+      b.lo[rank] = pos;
+      b.len[rank] = e - pos;
+      b.window[rank] = false;
+      b.dims[rank] = 1ull << (e - pos);
+      b.box[rank] = 1;
+      b.strides[rank] = 16ull << pos;
+      ++rank;
+    }
+    pos = e;
+  }
+  if (rank < 2) return b;
+  b.rank = rank;
+  return b;
+}
+
 struct Group {
   u32 lam, s1w, sBw;
   i64 so1, soB;
@@ -68,64 +171,14 @@ struct Group {
   u64 farmask;
 };
 
-void gen_pass(Out &o, const PassDesc &pd, int index)
+// acc[r] += D_g(row) * x[row ^ mask_g] for every group of the pass.  `tile` = the staged tile,
+// `x` = the global operand (far groups), `tid`, `og` (tile-uniform index bits) and `base` (this
+// thread's index without the row offsets) are in scope.
+void gen_groups(Out &o, const PassDesc &pd, const Geo &g_)
 {
   const PassParams &P = *pd.p;
   const SmallTables &S = *pd.st;
-  const int T = pd.T, R = 8, LOG_NT = T - 3, NT = 1 << LOG_NT;
-  const int minb = std::max(1, std::min(8, 65536 / (NT * 64)));
-  const std::vector<int> &W = pd.W;
-
-  i64 roff[8];
-  i64 rowbits = 0;
-  for (int r = 0; r < R; ++r) {
-    roff[r] = 0;
-    for (int k = 0; k < 3; ++k)
-      if ((r >> k) & 1) roff[r] |= (i64)1 << W[LOG_NT + k];
-  }
-  for (int k = 0; k < 3; ++k) rowbits |= (i64)1 << W[LOG_NT + k];
-
-  o("// ---- pass %d: T=%d, %d groups, %s, far_bits=%d\n", index, T, P.ngroups,
-    P.accumulate ? "accumulate" : "write", P.far_bits);
-  o("extern \"C\" __global__ void __launch_bounds__(%d, %d)\n", NT, minb);
-  o("dnm_jit_p%d(const double2 *__restrict__ x, double2 *__restrict__ y, const double *__restrict__ diag, i64 rank_bits)\n{\n",
-    index);
-  o("  extern __shared__ double2 tile[];\n");
-  o("  const u32 tid = threadIdx.x;\n");
-  o("  const u64 tb = blockIdx.x;\n");
-  // tile number -> index bits outside the window
-  {
-    std::string e;
-    if (P.n_seg >= 0) {
-      for (int j = 0; j < P.n_seg; ++j) {
-        char buf[160];
-        const int sh = P.seg_shift[j];
-        snprintf(buf, sizeof(buf), "((tb & 0x%llxull) %s %d)", (u64)P.seg_mask[j], sh >= 0 ? "<<" : ">>", sh >= 0 ? sh : -sh);
-        if (!e.empty()) e += " | ";
-        e += buf;
-      }
-    } else {
-      for (int k = 0; k < P.n_outer; ++k) {
-        char buf[160];
-        snprintf(buf, sizeof(buf), "(((tb >> %d) & 1ull) << %d)", k, (int)P.outer_pos[k]);
-        if (!e.empty()) e += " | ";
-        e += buf;
-      }
-    }
-    o("  const i64 outer = (i64)(%s);\n", e.empty() ? "0ull" : e.c_str());
-  }
-  o("  const i64 og = outer | rank_bits;  // index bits shared by the tile (signs)\n");
-  o("  const i64 base = outer | %s;\n", deposit_expr("tid", W, 0, LOG_NT).c_str());
-  // stage the tile
-  for (int r = 0; r < R; ++r) o("  cpa16(&tile[tid + %d], x + (base | 0x%llxll));\n", r * NT, (u64)roff[r]);
-  o("  cpa_wait();\n  __syncthreads();\n");
-  o("  double ar0, ai0, ar1, ai1, ar2, ai2, ar3, ai3, ar4, ai4, ar5, ai5, ar6, ai6, ar7, ai7;\n");
-  o("  if (diag != nullptr) {\n");
-  for (int r = 0; r < R; ++r)
-    o("    { const double d = __ldg(diag + (base | 0x%llxll)); const double2 v = tile[tid + %d]; ar%d = d * v.x; ai%d = d * v.y; }\n",
-      (u64)roff[r], r * NT, r, r);
-  o("  } else {\n    ar0 = ai0 = ar1 = ai1 = ar2 = ai2 = ar3 = ai3 = ar4 = ai4 = ar5 = ai5 = ar6 = ai6 = ar7 = ai7 = 0.0;\n  }\n");
-
+  const int R = g_.R, LOG_NT = g_.LOG_NT, NT = g_.NT;
   for (int g = 0; g < P.ngroups; ++g) {
     Group G;
     G.lam = S.lam[g];
@@ -146,12 +199,13 @@ void gen_pass(Out &o, const PassDesc &pd, int index)
     const int HI = (int)(G.lam >> LOG_NT);
     const u32 s1t = G.s1w & (u32)(NT - 1), sBt = G.sBw & (u32)(NT - 1);
     const u32 s1r = G.s1w >> LOG_NT, sBr = G.sBw >> LOG_NT;
+    // D(row) = (-1)^(e1 ^ k1(r)) * ((eB ^ kB(r)) ? c1 - c2 : c1 + c2): e = tile and thread part of the
+    // sign exponents (run time), k = row part (known here)
     const double A = G.c1 + G.c2, Bc = G.c1 - G.c2;
     if (A == 0.0 && Bc == 0.0) continue;
 
-    o("  {  // group %d: mask window 0x%x%s%s, c1=%s c2=%s\n", g, G.lam, G.imag ? " imag" : "", G.far ? " FAR" : "",
+    o("    {  // group %d: mask window 0x%x%s%s, c1=%s c2=%s\n", g, G.lam, G.imag ? " imag" : "", G.far ? " FAR" : "",
       hexd(G.c1).c_str(), hexd(G.c2).c_str());
-    // dynamic parts of the two sign exponents
     auto expo = [&](i64 so, u32 st) -> std::string {
       std::string e;
       char buf[128];
@@ -167,21 +221,16 @@ void gen_pass(Out &o, const PassDesc &pd, int index)
       return e;
     };
     const std::string e1 = expo(G.so1, s1t), eB = expo(G.soB, sBt);
-    if (!e1.empty()) o("    const int e1 = %s;\n", e1.c_str());
-    if (!eB.empty()) o("    const int eB = %s;\n", eB.c_str());
-    if (G.far) {
-      o("    const double2 *src = x + (base ^ 0x%llxll);\n", (u64)((i64)G.farmask & ~rowbits));
-    } else {
-      o("    const double2 *src = tile + (tid ^ 0x%xu);\n", lamlo);
-    }
-    // operand of row r
+    if (!e1.empty()) o("      const int e1 = %s;\n", e1.c_str());
+    if (!eB.empty()) o("      const int eB = %s;\n", eB.c_str());
+    if (G.far) o("      const double2 *src = x + (base ^ 0x%llxll);\n", (u64)((i64)G.farmask & ~g_.rowbits));
+    else o("      const double2 *src = tile + (tid ^ 0x%xu);\n", lamlo);
     auto operand = [&](int r) -> std::string {
       char buf[128];
-      if (G.far) snprintf(buf, sizeof(buf), "__ldcg(src + 0x%llxll)", (u64)roff[r ^ HI]);
+      if (G.far) snprintf(buf, sizeof(buf), "__ldcg(src + 0x%llxll)", (u64)g_.roff[r ^ HI]);
       else snprintf(buf, sizeof(buf), "src[%d]", (r ^ HI) * NT);
       return buf;
     };
-    // acc[r] += (+-) c * operand for the rows in `rows`, coefficient variable `cv`
     auto emit_rows = [&](const std::vector<int> &rows, const char *cv, const char *indent) {
       for (size_t h = 0; h < rows.size(); h += 4) {
         const size_t e = std::min(rows.size(), h + 4);
@@ -190,13 +239,12 @@ void gen_pass(Out &o, const PassDesc &pd, int index)
         for (size_t k = h; k < e; ++k) {
           const int r = rows[k];
           const bool neg = par32(s1r & (u32)r) != 0;
-          if (G.imag) {
+          if (G.imag)
             o("%s  ar%d = fma(%s%s, v%d.y, ar%d); ai%d = fma(%s%s, v%d.x, ai%d);\n", indent, r, neg ? "" : "-", cv, r, r, r,
               neg ? "-" : "", cv, r, r);
-          } else {
+          else
             o("%s  ar%d = fma(%s%s, v%d.x, ar%d); ai%d = fma(%s%s, v%d.y, ai%d);\n", indent, r, neg ? "-" : "", cv, r, r, r,
               neg ? "-" : "", cv, r, r);
-          }
         }
         o("%s}\n", indent);
       }
@@ -207,53 +255,228 @@ void gen_pass(Out &o, const PassDesc &pd, int index)
       (par32(sBr & (u32)r) ? rows1 : rows0).push_back(r);
     }
     if (G.c2 == 0.0) {
-      if (e1.empty()) o("    const double c = %s;\n", hexd(G.c1).c_str());
-      else o("    const double c = e1 ? %s : %s;\n", hexd(-G.c1).c_str(), hexd(G.c1).c_str());
-      emit_rows(all, "c", "    ");
+      if (e1.empty()) o("      const double c = %s;\n", hexd(G.c1).c_str());
+      else o("      const double c = e1 ? %s : %s;\n", hexd(-G.c1).c_str(), hexd(G.c1).c_str());
+      emit_rows(all, "c", "      ");
     } else if (A == 0.0 || Bc == 0.0) {
       // rows with (eB ^ kB(r)) == act carry +-V, the others vanish (XX+YY: half of the rows)
       const int act = (A == 0.0) ? 1 : 0;
       const double V = (A == 0.0) ? Bc : A;
-      if (e1.empty()) o("    const double c = %s;\n", hexd(V).c_str());
-      else o("    const double c = e1 ? %s : %s;\n", hexd(-V).c_str(), hexd(V).c_str());
+      if (e1.empty()) o("      const double c = %s;\n", hexd(V).c_str());
+      else o("      const double c = e1 ? %s : %s;\n", hexd(-V).c_str(), hexd(V).c_str());
       if (eB.empty()) {
-        emit_rows(act == 0 ? rows0 : rows1, "c", "    ");
+        emit_rows(act == 0 ? rows0 : rows1, "c", "      ");
       } else {
-        o("    if (eB == %d) {\n", act);
-        emit_rows(rows0, "c", "      ");
+        o("      if (eB == %d) {\n", act);
+        emit_rows(rows0, "c", "        ");
         if (!rows1.empty()) {
-          o("    } else {\n");
-          emit_rows(rows1, "c", "      ");
+          o("      } else {\n");
+          emit_rows(rows1, "c", "        ");
         }
-        o("    }\n");
+        o("      }\n");
       }
     } else {
-      // general pair: rows of class kB = 0 use (eB ? c1-c2 : c1+c2), class 1 the other one
-      const char *sgn = e1.empty() ? "" : "e1 ? -1.0 : 1.0";
-      if (eB.empty()) {
-        o("    double c0 = %s, c1v = %s;\n", hexd(A).c_str(), hexd(Bc).c_str());
-      } else {
-        o("    double c0 = eB ? %s : %s, c1v = eB ? %s : %s;\n", hexd(Bc).c_str(), hexd(A).c_str(), hexd(A).c_str(),
+      if (eB.empty()) o("      double c0 = %s, c1v = %s;\n", hexd(A).c_str(), hexd(Bc).c_str());
+      else
+        o("      double c0 = eB ? %s : %s, c1v = eB ? %s : %s;\n", hexd(Bc).c_str(), hexd(A).c_str(), hexd(A).c_str(),
           hexd(Bc).c_str());
-      }
-      if (!e1.empty()) o("    { const double sg = %s; c0 *= sg; c1v *= sg; }\n", sgn);
-      emit_rows(rows0, "c0", "    ");
-      if (!rows1.empty()) emit_rows(rows1, "c1v", "    ");
+      if (!e1.empty()) o("      if (e1) { c0 = -c0; c1v = -c1v; }\n");
+      emit_rows(rows0, "c0", "      ");
+      if (!rows1.empty()) emit_rows(rows1, "c1v", "      ");
     }
-    o("  }\n");
+    o("    }\n");
+  }
+}
+
+// streaming (evict-first) accesses for data that is touched once per pass (experiment knob DNM_JIT_HINTS=0)
+bool hints_on() { return !(getenv("DNM_JIT_HINTS") && atoi(getenv("DNM_JIT_HINTS")) == 0); }
+const char *hint_ld() { return hints_on() ? "__ldcs" : "__ldg"; }
+const char *hint_st() { return hints_on() ? "__stcs" : "st_plain"; }
+
+std::string acc_decl(int R)
+{
+  std::string s = "    double ";
+  for (int r = 0; r < R; ++r) {
+    char buf[32];
+    snprintf(buf, sizeof(buf), "%sar%d, ai%d", r ? ", " : "", r, r);
+    s += buf;
+  }
+  return s + ";\n";
+}
+
+// one tile per CTA, cp.async staging
+void gen_classic(Out &o, const PassDesc &pd, int index)
+{
+  const PassParams &P = *pd.p;
+  const Geo g(pd);
+  const int R = g.R, NT = g.NT;
+  const int minb = std::max(1, std::min(8, 65536 / (NT * 64)));
+  o("// ---- pass %d (classic): T=%d R=%d, %d groups, %s, far_bits=%d\n", index, g.T, R, P.ngroups,
+    P.accumulate ? "accumulate" : "write", P.far_bits);
+  o("extern \"C\" __global__ void __launch_bounds__(%d, %d)\n", NT, minb);
+  o("dnm_jit_p%d(const double2 *__restrict__ x, double2 *__restrict__ y, const double *__restrict__ diag, i64 rank_bits)\n{\n",
+    index);
+  o("  extern __shared__ double2 tile[];\n");
+  o("  const u32 tid = threadIdx.x;\n");
+  o("  const u64 tb = blockIdx.x;\n");
+  o("  {\n");
+  o("    const i64 outer = (i64)(%s);\n", outer_expr(P, "tb").c_str());
+  o("    const i64 og = outer | rank_bits;  // index bits shared by the tile (signs)\n");
+  o("    const i64 base = outer | %s;\n", deposit_expr("tid", pd.W, 0, g.LOG_NT).c_str());
+  for (int r = 0; r < R; ++r) o("    cpa16(&tile[tid + %d], x + (base | 0x%llxll));\n", r * NT, (u64)g.roff[r]);
+  // the cached diagonal is in flight together with the tile
+  for (int r = 0; r < R; ++r) o("    double dg%d = 0.0;\n", r);
+  o("    if (diag != nullptr) {\n");
+  for (int r = 0; r < R; ++r) o("      dg%d = %s(diag + (base | 0x%llxll));\n", r, hint_ld(), (u64)g.roff[r]);
+  o("    }\n");
+  o("    cpa_wait();\n    __syncthreads();\n");
+  o("%s", acc_decl(R).c_str());
+  for (int r = 0; r < R; ++r)
+    o("    { const double2 v = tile[tid + %d]; ar%d = dg%d * v.x; ai%d = dg%d * v.y; }\n", r * NT, r, r, r, r);
+  gen_groups(o, pd, g);
+  if (P.accumulate == 1) {
+    o("    __syncthreads();\n");
+    for (int r = 0; r < R; ++r) o("    cpa16(&tile[tid + %d], y + (base | 0x%llxll));\n", r * NT, (u64)g.roff[r]);
+    o("    cpa_wait();\n");
+    for (int r = 0; r < R; ++r)
+      o("    { const double2 old = tile[tid + %d]; y[base | 0x%llxll] = make_double2(ar%d + old.x, ai%d + old.y); }\n", r * NT,
+        (u64)g.roff[r], r, r);
+  } else {
+    for (int r = 0; r < R; ++r) o("    %s(y + (base | 0x%llxll), make_double2(ar%d, ai%d));\n", hint_st(), (u64)g.roff[r], r, r);
+  }
+  o("  }\n}\n\n");
+}
+
+int pipelined_ctas(const PassDesc &pd)
+{
+  const Geo g(pd);
+  const size_t bytes = (size_t)(pd.nbuf + (pd.p->accumulate == 1 ? 1 : 0)) * ((size_t)16 << pd.T) + 1024 + 1024;
+  int by_smem = (int)(232448 / bytes);
+  int by_threads = 2048 / g.NT;
+  return std::max(1, std::min(std::min(by_smem, by_threads), 4));
+}
+
+// persistent CTAs, TMA ring, reduce-add epilogue
+void gen_pipelined(Out &o, const PassDesc &pd, int index)
+{
+  const PassParams &P = *pd.p;
+  const Geo g(pd);
+  const Box bx = tile_box(pd);
+  const int R = g.R, NT = g.NT, T = g.T;
+  const bool reduce = P.accumulate == 1;
+  const int ctas = pipelined_ctas(pd);
+  const u32 tile_bytes = 16u << T;
+  o("// ---- pass %d (pipelined): T=%d R=%d nbuf=%d, %d groups, %s, far_bits=%d, TMA rank %d\n", index, T, R, pd.nbuf, P.ngroups,
+    reduce ? "accumulate (reduce-add)" : "write", P.far_bits, bx.rank);
+  o("__device__ __forceinline__ i64 outer_p%d(u64 tb) { return (i64)(%s); }\n", index, outer_expr(P, "tb").c_str());
+  auto coords = [&]() -> std::string {
+    std::string c;
+    for (int d = 0; d < bx.rank; ++d) {
+      char buf[96];
+      if (bx.window[d]) snprintf(buf, sizeof(buf), "0");
+      else snprintf(buf, sizeof(buf), "(int)(((u64)outer >> %d) & 0x%llxull)", bx.lo[d], (1ull << bx.len[d]) - 1ull);
+      if (d) c += ", ";
+      c += buf;
+    }
+    return c;
+  };
+  // issue the TMA load of tile `tb` into ring buffer `dst`
+  o("__device__ __forceinline__ void load_p%d(const TMap *tmx, const double2 *x, u64 tb, void *dst, u64 *bar)\n{\n", index);
+  o("  const i64 outer = outer_p%d(tb);\n", index);
+  o("  mbar_expect_tx(bar, %uu);\n", tile_bytes);
+  if (bx.rank == 0) {
+    o("  asm volatile(\"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%%0], [%%1], %%2, [%%3];\" "
+      "::\"r\"(smem_u32(dst)), \"l\"(x + outer), \"r\"(%uu), \"r\"(smem_u32(bar)) : \"memory\");\n",
+      tile_bytes);
+  } else {
+    std::string ops, cl;
+    for (int d = 0; d < bx.rank; ++d) {
+      char buf[32];
+      snprintf(buf, sizeof(buf), "%s%%%d", d ? ", " : "", 3 + d);
+      ops += buf;
+      snprintf(buf, sizeof(buf), ", \"r\"(c[%d])", d);
+      cl += buf;
+    }
+    o("  const int c[%d] = {%s};\n", bx.rank, coords().c_str());
+    o("  asm volatile(\"cp.async.bulk.tensor.%dd.shared::cluster.global.mbarrier::complete_tx::bytes [%%0], [%%1, {%s}], [%%2];\" "
+      "::\"r\"(smem_u32(dst)), \"l\"(tmx), \"r\"(smem_u32(bar))%s : \"memory\");\n",
+      bx.rank, ops.c_str(), cl.c_str());
+  }
+  o("}\n");
+  if (reduce) {
+    o("__device__ __forceinline__ void reduce_p%d(const TMap *tmy, u64 tb, const void *src)\n{\n", index);
+    o("  const i64 outer = outer_p%d(tb);\n", index);
+    std::string ops, cl;
+    for (int d = 0; d < bx.rank; ++d) {
+      char buf[32];
+      snprintf(buf, sizeof(buf), "%s%%%d", d ? ", " : "", 2 + d);
+      ops += buf;
+      snprintf(buf, sizeof(buf), ", \"r\"(c[%d])", d);
+      cl += buf;
+    }
+    o("  const int c[%d] = {%s};\n", bx.rank, coords().c_str());
+    o("  asm volatile(\"cp.reduce.async.bulk.tensor.%dd.global.shared::cta.add.bulk_group [%%0, {%s}], [%%1];\" "
+      "::\"l\"(tmy), \"r\"(smem_u32(src))%s : \"memory\");\n",
+      bx.rank, ops.c_str(), cl.c_str());
+    o("  asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");\n}\n");
   }
 
-  // epilogue
-  if (P.accumulate == 1) {
-    o("  __syncthreads();\n");
-    for (int r = 0; r < R; ++r) o("  cpa16(&tile[tid + %d], y + (base | 0x%llxll));\n", r * NT, (u64)roff[r]);
-    o("  cpa_wait();\n");
-    for (int r = 0; r < R; ++r)
-      o("  { const double2 old = tile[tid + %d]; y[base | 0x%llxll] = make_double2(ar%d + old.x, ai%d + old.y); }\n", r * NT,
-        (u64)roff[r], r, r);
+  o("extern \"C\" __global__ void __launch_bounds__(%d, %d)\n", NT, ctas);
+  o("dnm_jit_p%d(const __grid_constant__ TMap tmx, const __grid_constant__ TMap tmy, const double2 *__restrict__ x,\n"
+    "           double2 *__restrict__ y, const double *__restrict__ diag, i64 rank_bits, u64 ntiles)\n{\n",
+    index);
+  o("  extern __shared__ __align__(1024) unsigned char smem[];\n");
+  o("  double2 *ring = reinterpret_cast<double2 *>(smem);\n");
+  if (reduce) o("  double2 *outb = ring + %d;\n", pd.nbuf << T);
+  o("  u64 *full = reinterpret_cast<u64 *>(smem + %zu);\n", (size_t)(pd.nbuf + (reduce ? 1 : 0)) * tile_bytes);
+  o("  const u32 tid = threadIdx.x;\n");
+  o("  const u64 stride = gridDim.x;\n");
+  o("  if (tid == 0) {\n");
+  for (int b = 0; b < pd.nbuf; ++b) o("    mbar_init(&full[%d], 1);\n", b);
+  o("    asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\");\n");
+  o("  }\n  __syncthreads();\n");
+  o("  if (tid == 0) {\n    u64 tt = blockIdx.x;\n");
+  o("    for (int b = 0; b < %d && tt < ntiles; ++b, tt += stride) load_p%d(&tmx, x, tt, ring + ((size_t)b << %d), &full[b]);\n",
+    pd.nbuf, index, T);
+  o("  }\n");
+  o("  const i64 toff = %s;\n", deposit_expr("tid", pd.W, 0, g.LOG_NT).c_str());
+  // software-pipelined diagonal: the values of the next tile are fetched while this one is evaluated
+  for (int r = 0; r < R; ++r) o("  double dn%d = 0.0;\n", r);
+  o("  if (diag != nullptr && blockIdx.x < ntiles) {\n    const i64 nb = outer_p%d(blockIdx.x) | toff;\n", index);
+  for (int r = 0; r < R; ++r) o("    dn%d = %s(diag + (nb | 0x%llxll));\n", r, hint_ld(), (u64)g.roff[r]);
+  o("  }\n");
+  o("  int b = 0;\n  u32 phase = 0;\n");
+  o("  for (u64 tb = blockIdx.x; tb < ntiles; tb += stride) {\n");
+  o("    const i64 outer = outer_p%d(tb);\n", index);
+  o("    const i64 og = outer | rank_bits;  // index bits shared by the tile (signs)\n");
+  o("    const i64 base = outer | toff;\n");
+  for (int r = 0; r < R; ++r) o("    const double dg%d = dn%d;\n", r, r);
+  o("    if (diag != nullptr && tb + stride < ntiles) {\n      const i64 nb = outer_p%d(tb + stride) | toff;\n", index);
+  for (int r = 0; r < R; ++r) o("      dn%d = %s(diag + (nb | 0x%llxll));\n", r, hint_ld(), (u64)g.roff[r]);
+  o("    }\n");
+  o("    mbar_wait(&full[b], phase);\n");
+  o("    const double2 *tile = ring + ((size_t)b << %d);\n", T);
+  o("%s", acc_decl(R).c_str());
+  for (int r = 0; r < R; ++r)
+    o("    { const double2 v = tile[tid + %d]; ar%d = dg%d * v.x; ai%d = dg%d * v.y; }\n", r * NT, r, r, r, r);
+  gen_groups(o, pd, g);
+  if (reduce) {
+    o("    if (tid == 0) asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");  // the staging buffer is free again\n");
+    o("    __syncthreads();\n");
+    for (int r = 0; r < R; ++r) o("    outb[tid + %d] = make_double2(ar%d, ai%d);\n", r * NT, r, r);
+    o("    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n");
+    o("    __syncthreads();\n");
+    o("    if (tid == 0) {\n      reduce_p%d(&tmy, tb, outb);\n", index);
   } else {
-    for (int r = 0; r < R; ++r) o("  y[base | 0x%llxll] = make_double2(ar%d, ai%d);\n", (u64)roff[r], r, r);
+    for (int r = 0; r < R; ++r) o("    %s(y + (base | 0x%llxll), make_double2(ar%d, ai%d));\n", hint_st(), (u64)g.roff[r], r, r);
+    o("    __syncthreads();  // nobody reads ring[b] any more\n");
+    o("    if (tid == 0) {\n");
   }
+  o("      const u64 tn = tb + %dull * stride;\n", pd.nbuf);
+  o("      if (tn < ntiles) load_p%d(&tmx, x, tn, ring + ((size_t)b << %d), &full[b]);\n    }\n", index, T);
+  o("    if (++b == %d) { b = 0; phase ^= 1u; }\n", pd.nbuf);
+  o("  }\n");
+  if (reduce) o("  if (tid == 0) asm volatile(\"cp.async.bulk.wait_group 0;\" ::: \"memory\");\n");
   o("}\n\n");
 }
 
@@ -293,6 +516,10 @@ Nvrtc &nvrtc()
   return n;
 }
 
+typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                             const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
 struct Driver {
   CUresult (*moduleLoadData)(CUmodule *, const void *) = nullptr;
   CUresult (*moduleGetFunction)(CUfunction *, CUmodule, const char *) = nullptr;
@@ -300,6 +527,7 @@ struct Driver {
   CUresult (*funcSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
   CUresult (*launchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **,
                            void **) = nullptr;
+  EncodeFn encode = nullptr;
   bool ok = false;
 };
 
@@ -322,22 +550,41 @@ Driver &driver()
     d.moduleUnload = (decltype(d.moduleUnload))get("cuModuleUnload");
     d.funcSetAttribute = (decltype(d.funcSetAttribute))get("cuFuncSetAttribute");
     d.launchKernel = (decltype(d.launchKernel))get("cuLaunchKernel");
-    d.ok = d.moduleLoadData && d.moduleGetFunction && d.moduleUnload && d.funcSetAttribute && d.launchKernel;
+    d.encode = (EncodeFn)get("cuTensorMapEncodeTiled");
+    d.ok = d.moduleLoadData && d.moduleGetFunction && d.moduleUnload && d.funcSetAttribute && d.launchKernel && d.encode;
   });
   return d;
 }
 
+const char *PRELUDE =
+    "// generated by dynamite_b200 (csrc/jit.cu): operator-specialised window-tiled MatMult passes\n"
+    "typedef long long i64;\ntypedef unsigned long long u64;\ntypedef unsigned int u32;\n"
+    "struct __align__(64) TMap { u64 opaque[16]; };\n"
+    "__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }\n"
+    "__device__ __forceinline__ void cpa16(void *s, const void *g)\n{\n"
+    "  asm volatile(\"cp.async.cg.shared.global [%0], [%1], 16;\\n\" ::\"r\"(smem_u32(s)), \"l\"(g) : \"memory\");\n}\n"
+    "__device__ __forceinline__ void cpa_wait() { asm volatile(\"cp.async.commit_group;\\ncp.async.wait_group 0;\\n\" ::: \"memory\"); }\n"
+    "__device__ __forceinline__ void st_plain(double2 *p, double2 v) { *p = v; }\n"
+    "__device__ __forceinline__ void mbar_init(u64 *bar, int count)\n{\n"
+    "  asm volatile(\"mbarrier.init.shared::cta.b64 [%0], %1;\" ::\"r\"(smem_u32(bar)), \"r\"(count));\n}\n"
+    "__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)\n{\n"
+    "  asm volatile(\"mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\" ::\"r\"(smem_u32(bar)), \"r\"(bytes) : \"memory\");\n}\n"
+    "__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)\n{\n"
+    "  asm volatile(\"{\\n.reg .pred p;\\nWAIT_%=:\\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\\n@p bra DONE_%=;\\nbra "
+    "WAIT_%=;\\nDONE_%=:\\n}\\n\" ::\"r\"(smem_u32(bar)), \"r\"(parity) : \"memory\");\n}\n\n";
+
 }  // namespace
 
-std::string generate(const std::vector<PassDesc> &passes, int)
+bool tma_eligible(const PassDesc &pd) { return tile_box(pd).rank >= 0; }
+
+std::string generate(const std::vector<PassDesc> &passes)
 {
   Out o;
-  o("// generated by dynamite_b200 (csrc/jit.cu): operator-specialised window-tiled MatMult passes\n");
-  o("typedef long long i64;\ntypedef unsigned long long u64;\ntypedef unsigned int u32;\n");
-  o("__device__ __forceinline__ void cpa16(void *s, const void *g)\n{\n"
-    "  asm volatile(\"cp.async.cg.shared.global [%%0], [%%1], 16;\\n\" ::\"r\"((u32)__cvta_generic_to_shared(s)), \"l\"(g) : \"memory\");\n}\n");
-  o("__device__ __forceinline__ void cpa_wait() { asm volatile(\"cp.async.commit_group;\\ncp.async.wait_group 0;\\n\" ::: \"memory\"); }\n\n");
-  for (size_t k = 0; k < passes.size(); ++k) gen_pass(o, passes[k], (int)k);
+  o.s = PRELUDE;
+  for (size_t k = 0; k < passes.size(); ++k) {
+    if (passes[k].pipelined) gen_pipelined(o, passes[k], (int)k);
+    else gen_classic(o, passes[k], (int)k);
+  }
   return o.s;
 }
 
@@ -354,8 +601,8 @@ std::vector<char> compile_cubin(const std::string &src, std::string &log)
     log = "nvrtcCreateProgram failed";
     return cubin;
   }
-  const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--extra-device-vectorization"};
-  const int rc = n.compile(prog, 4, opts);
+  const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+  const int rc = n.compile(prog, 3, opts);
   size_t ls = 0;
   n.log_size(prog, &ls);
   if (ls > 1) {
@@ -378,10 +625,10 @@ Module::~Module()
   if (mod && driver().ok) driver().moduleUnload((CUmodule)mod);
 }
 
-Module *compile(const std::string &src, const std::vector<PassDesc> &passes, std::string &log, bool load)
+Module *compile(const std::string &src, const std::vector<PassDesc> &passes, std::string &log)
 {
   const std::vector<char> cubin = compile_cubin(src, log);
-  if (cubin.empty() || !load) return nullptr;
+  if (cubin.empty()) return nullptr;
   Driver &d = driver();
   if (!d.ok) {
     log += " [driver entry points unavailable]";
@@ -396,6 +643,7 @@ Module *compile(const std::string &src, const std::vector<PassDesc> &passes, std
   Module *m = new Module();
   m->mod = mod;
   for (size_t k = 0; k < passes.size(); ++k) {
+    const PassDesc &pd = passes[k];
     Kernel kn;
     const std::string name = "dnm_jit_p" + std::to_string(k);
     CUfunction f = nullptr;
@@ -405,9 +653,26 @@ Module *compile(const std::string &src, const std::vector<PassDesc> &passes, std
       delete m;
       return nullptr;
     }
+    const Geo g(pd);
+    static unsigned long long next_uid = 1;
+    kn.uid = next_uid++;
     kn.func = f;
-    kn.smem = sizeof(double2) << passes[k].T;
-    kn.threads = 1 << (passes[k].T - 3);
+    kn.threads = g.NT;
+    kn.pipelined = pd.pipelined;
+    if (pd.pipelined) {
+      const Box bx = tile_box(pd);
+      kn.reduce = pd.p->accumulate == 1;
+      kn.smem = (size_t)(pd.nbuf + (kn.reduce ? 1 : 0)) * ((size_t)16 << pd.T) + 128;
+      kn.ctas_per_sm = pipelined_ctas(pd);
+      kn.rank = bx.rank;
+      for (int i = 0; i < bx.rank; ++i) {
+        kn.dims[i] = bx.dims[i];
+        kn.strides[i] = bx.strides[i];
+        kn.box[i] = bx.box[i];
+      }
+    } else {
+      kn.smem = (size_t)16 << pd.T;
+    }
     d.funcSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)kn.smem);
     d.funcSetAttribute(f, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100);
     m->kernels.push_back(kn);
@@ -415,12 +680,62 @@ Module *compile(const std::string &src, const std::vector<PassDesc> &passes, std
   return m;
 }
 
-void launch(const Kernel &k, unsigned long long ntiles, cudaStream_t stream, const cplx *x, cplx *y, const double *diag,
-            long long rank_bits)
+namespace {
+
+// tensor maps are pure functions of (kernel geometry, base pointer): keep the last few
+struct MapCache {
+  const void *ptr[8];
+  unsigned long long uid[8];
+  CUtensorMap map[8];
+  int next = 0, used = 0;
+};
+
+const CUtensorMap *tensor_map(const Kernel &k, const void *ptr)
 {
-  void *args[] = {(void *)&x, (void *)&y, (void *)&diag, (void *)&rank_bits};
-  const CUresult rc = driver().launchKernel((CUfunction)k.func, (unsigned)ntiles, 1, 1, (unsigned)k.threads, 1, 1,
-                                            (unsigned)k.smem, (CUstream)stream, args, nullptr);
+  static MapCache cache;
+  for (int i = 0; i < cache.used; ++i)
+    if (cache.ptr[i] == ptr && cache.uid[i] == k.uid) return &cache.map[i];
+  const int slot = cache.next;
+  cache.next = (cache.next + 1) % 8;
+  cache.used = std::min(cache.used + 1, 8);
+  cuuint64_t dims[MAX_TMA_RANK], strides[MAX_TMA_RANK];
+  cuuint32_t box[MAX_TMA_RANK], estr[MAX_TMA_RANK];
+  for (int i = 0; i < k.rank; ++i) {
+    dims[i] = k.dims[i];
+    box[i] = k.box[i];
+    estr[i] = 1;
+    if (i > 0) strides[i - 1] = k.strides[i];
+  }
+  cache.ptr[slot] = nullptr;
+  const CUresult rc = driver().encode(&cache.map[slot], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)k.rank,
+                                      const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DNM_REQUIRE(rc == CUDA_SUCCESS, DNM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+  cache.ptr[slot] = ptr;
+  cache.uid[slot] = k.uid;
+  return &cache.map[slot];
+}
+
+}  // namespace
+
+void launch(const Kernel &k, unsigned long long ntiles, int sm_count, cudaStream_t stream, const cplx *x, cplx *y,
+            const double *diag, long long rank_bits, long long)
+{
+  CUresult rc;
+  if (k.pipelined) {
+    static const CUtensorMap zero = {};
+    const CUtensorMap *tmx = k.rank > 0 ? tensor_map(k, x) : &zero;
+    const CUtensorMap *tmy = (k.rank > 0 && k.reduce) ? tensor_map(k, y) : &zero;
+    const unsigned grid = (unsigned)std::min<unsigned long long>(ntiles, (unsigned long long)sm_count * k.ctas_per_sm);
+    void *args[] = {(void *)tmx, (void *)tmy, (void *)&x, (void *)&y, (void *)&diag, (void *)&rank_bits, (void *)&ntiles};
+    rc = driver().launchKernel((CUfunction)k.func, grid, 1, 1, (unsigned)k.threads, 1, 1, (unsigned)k.smem, (CUstream)stream, args,
+                               nullptr);
+  } else {
+    void *args[] = {(void *)&x, (void *)&y, (void *)&diag, (void *)&rank_bits};
+    rc = driver().launchKernel((CUfunction)k.func, (unsigned)ntiles, 1, 1, (unsigned)k.threads, 1, 1, (unsigned)k.smem,
+                               (CUstream)stream, args, nullptr);
+  }
   DNM_REQUIRE(rc == CUDA_SUCCESS, DNM_ERR_CUDA, "cuLaunchKernel of a generated MatMult pass failed (%d)", (int)rc);
 }
 

@@ -899,7 +899,8 @@ int rows_for(int T, int want)
 void launch_pass(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64 ntiles)
 {
   if (ps.jk) {
-    jit::launch(*ps.jk, (unsigned long long)ntiles, launch_stream(), x, y, diag, (long long)ps.p.rank_bits);
+    jit::launch(*ps.jk, (unsigned long long)ntiles, G.sm_count, launch_stream(), x, y, diag, (long long)ps.p.rank_bits,
+                (long long)ntiles << ps.T);
     count_launch();
     return;
   }
@@ -1034,7 +1035,8 @@ TiledPlan::Need stage_need(const std::vector<const NMask *> &masks, int nloc)
 }
 
 // One candidate plan for a fixed tile size T and run length 2^B.
-std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &masks, int T, int R, int B, int verbose)
+std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &masks, int T, int R, int B, int fmax_in,
+                                     int verbose)
 {
   std::unique_ptr<TiledPlan> plan(new TiledPlan());
   const int n = ilog2(A->M);
@@ -1080,13 +1082,8 @@ std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &mas
     plan->dma = groups.size() > 1 && mode == "dma";
     plan->overlap = groups.size() > 1 && mode == "peer_overlap";
     bool first_local = true, first_remote = true;
-    // L2 window (FAR masks): option far_bits, -1 = auto
-    int fmax = A->far_bits;
-    if (fmax < 0) {
-      fmax = 0;
-      if (const char *e = getenv("DNM_FAR_BITS")) fmax = atoi(e);
-    }
-    fmax = std::max(0, std::min(fmax, nloc - T));
+    // L2 window (FAR masks)
+    const int fmax = std::max(0, std::min(fmax_in, nloc - T));
     for (auto &kv : groups) {
       if (kv.first == 0) {
         plan_group(*plan, kv.second, kv.first, T, R, B, first_local, verbose, fmax);
@@ -1133,38 +1130,85 @@ TiledPlan *build_plan(dnm_mat_s *A)
   const int nloc = n - ilog2(G.nranks);
   const std::vector<NMask> masks = normalise(A, n);  // only needed while planning: plans own device copies
 
-  std::vector<std::pair<int, int>> candidates;  // (T, B)
+  struct Cand {
+    int T, B, f;
+    bool for_jit;
+  };
+  std::vector<Cand> candidates;
   const char *env_b = getenv("DNM_TILE_RUN_BITS");
-  // Measured on B200 (profiles/r01_explore_tiles.log, r01_ring_experiment.md): up to 2^28 rows per
-  // GPU 64 KB tiles (T=12, two CTAs per SM) win; beyond that 128 KB tiles (T=13, one pass fewer
-  // over HBM) do -- 64 KB tiles would need 64-byte runs there, which thrash at 16 MB strides.
-  std::vector<int> Ts = A->tile_bits ? std::vector<int>{A->tile_bits}
-                                     : (nloc >= 29 ? std::vector<int>{13} : std::vector<int>{12});
-  std::vector<int> Bs = env_b ? std::vector<int>{atoi(env_b)} : std::vector<int>{3, 2};
-  for (int T : Ts)
-    for (int B : Bs) {
-      T = std::min(T, nloc);
-      B = std::max(0, std::min(B, T - 1));
-      B = std::min(B, T - 4);  // a thread's own index bits (>= T-4 of them) must cover the run bits
-      if (std::find(candidates.begin(), candidates.end(), std::make_pair(T, B)) == candidates.end())
-        candidates.emplace_back(T, B);
-    }
+  int far_opt = A->far_bits;
+  if (far_opt < 0 && getenv("DNM_FAR_BITS")) far_opt = atoi(getenv("DNM_FAR_BITS"));
+  const bool jit_possible = A->jit != 0 && getenv("DNM_NO_JIT") == nullptr && (A->jit == 1 || nloc >= 22);
+  // Generic kernel (profiles/r01_explore_tiles.log, r01_ring_experiment.md): up to 2^28 rows per GPU
+  // 64 KB tiles (T=12, two CTAs per SM) win; beyond that 128 KB tiles (T=13, one pass fewer over HBM).
+  {
+    std::vector<int> Ts = A->tile_bits ? std::vector<int>{A->tile_bits}
+                                       : (nloc >= 29 ? std::vector<int>{13} : std::vector<int>{12});
+    std::vector<int> Bs = env_b ? std::vector<int>{atoi(env_b)} : std::vector<int>{3, 2};
+    for (int T : Ts)
+      for (int B : Bs) {
+        T = std::min(T, nloc);
+        B = std::max(0, std::min(B, T - 1));
+        B = std::min(B, T - 4);  // a thread's own index bits (>= T-4 of them) must cover the run bits
+        bool seen = false;
+        for (const Cand &c : candidates) seen = seen || (c.T == T && c.B == B);
+        if (!seen) candidates.push_back(Cand{T, B, std::max(far_opt, 0), false});
+      }
+  }
+  // Generated kernels (profiles/r02_jit_*): 32 KB tiles (T=11, four CTAs per SM hide the L2 latency of
+  // the FAR loads), an L2 window of up to 10 positions (two passes instead of three or four at L=30) and
+  // 256-byte runs (128-byte runs reach 4.8 TB/s in an accumulating pass, 256-byte runs 6.2 TB/s:
+  // scripts/micro/tma_stream.cu).
+  if (jit_possible && !A->tile_bits && far_opt < 0 && nloc >= 15) {
+    const int B = env_b ? std::max(0, std::min(atoi(env_b), 7)) : 4;
+    candidates.push_back(Cand{11, B, std::min(10, nloc - 11), true});
+  }
   std::unique_ptr<TiledPlan> best;
-  for (auto &tb : candidates) {
-    std::unique_ptr<TiledPlan> cand = plan_with(A, masks, tb.first, rows_for(tb.first, A->tile_rows), tb.second, A->verbose);
+  Cand best_c{0, 0, 0, false};
+  for (const Cand &c : candidates) {
+    std::unique_ptr<TiledPlan> cand = plan_with(A, masks, c.T, rows_for(c.T, A->tile_rows), c.B, c.f, A->verbose);
     if (A->verbose)
-      fprintf(stderr, "[dnm] plan T=%d B=%d: %zu passes + %zu direct, cost %.2f sweeps\n", tb.first, tb.second,
+      fprintf(stderr, "[dnm] plan T=%d B=%d far<=%d: %zu passes + %zu direct, cost %.2f sweeps\n", c.T, c.B, c.f,
               cand->passes.size(), cand->directs.size(), cand->cost);
-    if (!best || cand->cost < best->cost - 1e-9) best = std::move(cand);
+    if (c.for_jit) {
+      // only worth it when every pass can run a generated kernel and no pass is added
+      bool lean = cand->directs.empty();
+      for (const Pass &ps : cand->passes) lean = lean && ps.small && ps.p.lean && ps.R == 8;
+      if (!lean || (best && cand->passes.size() > best->passes.size())) continue;
+      best = std::move(cand);
+      best_c = c;
+      continue;
+    }
+    if (!best || cand->cost < best->cost - 1e-9) {
+      best = std::move(cand);
+      best_c = c;
+    }
+  }
+  // the batched launch below interprets its passes with the table-driven group loop, which has no FAR
+  // path: small problems are planned without an L2 window
+  auto batchable = [&](const TiledPlan &pl) {
+    if (!(G.nranks == 1 && pl.directs.empty() && pl.passes.size() >= 3 && getenv("DNM_NO_BATCH") == nullptr)) return false;
+    const Pass &p0 = pl.passes[0];
+    bool same = true;
+    for (const Pass &ps : pl.passes) same = same && ps.T == p0.T && ps.R == p0.R && ps.peer_xor == 0;
+    return same && ((long long)1 << (pl.nloc - p0.T)) <= 4LL * G.sm_count && pl.passes.size() < 65536;
+  };
+  if (best && best_c.f > 0) {
+    bool any_far = false;
+    for (const Pass &ps : best->passes) any_far = any_far || ps.nfar > 0;
+    if (any_far) {
+      std::unique_ptr<TiledPlan> plain = plan_with(A, masks, best_c.T, rows_for(best_c.T, A->tile_rows), best_c.B, 0, 0);
+      if (batchable(*plain) && A->jit != 1) best = std::move(plain);
+    }
   }
   // Small problems (a pass has fewer tiles than the GPU has CTA slots) with several passes: run all
   // passes concurrently as one grid and combine in y with FP64 atomics.
-  if (best && G.nranks == 1 && best->directs.empty() && best->passes.size() >= 3 && getenv("DNM_NO_BATCH") == nullptr) {
+  bool has_far = false;
+  if (best)
+    for (const Pass &ps : best->passes) has_far = has_far || ps.nfar > 0;
+  if (best && !has_far && A->jit != 1 && batchable(*best)) {
     const Pass &p0 = best->passes[0];
-    const long long ntiles = (long long)1 << (best->nloc - p0.T);
-    bool same = true;
-    for (const Pass &ps : best->passes) same = same && ps.T == p0.T && ps.R == p0.R && ps.peer_xor == 0;
-    if (same && ntiles <= 4LL * G.sm_count && best->passes.size() < 65536) {
+    {
       std::vector<PassParams> all;
       for (const Pass &ps : best->passes) {
         PassParams q = ps.p;
@@ -1193,20 +1237,33 @@ TiledPlan *build_plan(dnm_mat_s *A)
       d.p = &ps.p;
       d.st = &ps.st;
       d.T = ps.T;
+      d.nloc = best->nloc;
       d.W = ps.W;
+      d.rows = 8;
+      if (const char *e = getenv("DNM_JIT_ROWS")) d.rows = atoi(e) == 4 ? 4 : 8;
+      d.nbuf = ps.p.accumulate == 1 ? 2 : 3;
+      if (const char *e = getenv("DNM_JIT_NBUF")) d.nbuf = std::max(2, std::min(6, atoi(e)));
+      // pipelined (persistent, TMA ring, reduce-add epilogue) wherever the tile is a TMA box and the ring fits;
+      // remote operands that are read through peer mappings keep the classic kernel
+      const size_t ring = (size_t)(d.nbuf + (ps.p.accumulate == 1 ? 1 : 0)) * ((size_t)16 << ps.T) + 2048;
+      // Measured on B200 (profiles/r02_pipelined_experiment.md): with 8-16 resident warps per SM the
+      // persistent kernel cannot hide the L2 latency of the FAR loads and loses to one tile per CTA
+      // (4 CTAs per SM at T=11); it stays opt-in (option pipeline = 1).
+      d.pipelined = A->pipeline == 1 && jit::tma_eligible(d) &&
+                    ring <= 232448 && (ps.peer_xor == 0 || best->dma);
       descs.push_back(d);
       which.push_back(k);
     }
     if (!descs.empty()) {
       std::string log;
-      const std::string src = jit::generate(descs, 0);
+      const std::string src = jit::generate(descs);
       if (const char *dump = getenv("DNM_JIT_DUMP")) {
         if (FILE *f = fopen(dump, "w")) {
           fwrite(src.data(), 1, src.size(), f);
           fclose(f);
         }
       }
-      best->jit = jit::compile(src, descs, log, true);
+      best->jit = jit::compile(src, descs, log);
       if (best->jit) {
         for (size_t k = 0; k < which.size(); ++k) best->passes[which[k]].jk = &best->jit->kernels[k];
         if (A->verbose) fprintf(stderr, "[dnm] %zu generated kernels (%zu bytes of source)\n", which.size(), src.size());

@@ -26,6 +26,7 @@ for tb, far, *rest in [tuple(int(v) for v in a.split(',')) for a in sys.argv[3:]
     mat.set_option('tile_bits', tb)
     mat.set_option('far_bits', far)
     mat.set_option('jit', rest[0] if rest else 0)
+    mat.set_option('pipeline', rest[1] if len(rest) > 1 else 0)
     t0 = time.perf_counter()
     mat.mult(x, y); lib.dnm_synchronize()
     t_first = time.perf_counter() - t0
@@ -37,5 +38,5 @@ for tb, far, *rest in [tuple(int(v) for v in a.split(',')) for a in sys.argv[3:]
         mat.mult(x, y0); err = 0.0; first = False
     else:
         y.axpy(-1.0, y0); err = y.norm() / y0.norm()
-    print(f'{model} L={L} T={tb} far={far} jit={mat.get_info("jit_passes"):.0f} passes={mat.get_info("passes"):.0f} first={t_first:.2f}s {ms.value/reps:.3f} ms  diff_vs_first={err:.2e}', flush=True)
+    print(f'{model} L={L} T={tb} far={far} pipe={rest[1] if len(rest) > 1 else 0} jit={mat.get_info("jit_passes"):.0f} passes={mat.get_info("passes"):.0f} first={t_first:.2f}s {ms.value/reps:.3f} ms  diff_vs_first={err:.2e}', flush=True)
     mat.destroy()
