@@ -258,6 +258,61 @@ def run_reference(args, rank, world):
     emit(out)
 
 
+XP = 1 << 20   # period of the low factor of the analytic input vector
+
+
+_FACTORS = {}
+
+
+def host_x_factors(n):
+    if n in _FACTORS:
+        return _FACTORS[n]
+    rs = np.random.RandomState(1234)
+    base = (rs.standard_normal(XP) + 1j * rs.standard_normal(XP)) / math.sqrt(2.0 * n)
+    w = np.exp(2j * np.pi * rs.random_sample(max(1, n // XP)))
+    _FACTORS[n] = (base, w)
+    return base, w
+
+
+def host_x(first, count, n):
+    """x[first : first+count] of the analytic input (count <= XP, inside one period)"""
+    base, w = host_x_factors(n)
+    lo = first % XP
+    assert lo + count <= XP
+    return base[lo:lo + count] * w[first // XP]
+
+
+def fill_host_x(xh, first, n):
+    base, w = host_x_factors(n)
+    if xh.size < XP:
+        xh[:] = host_x(first, xh.size, n)
+        return
+    blocks = xh.reshape(-1, XP)
+    step = 256
+    for b0 in range(0, blocks.shape[0], step):
+        np.multiply(w[first // XP + b0: first // XP + b0 + step, None], base[None, :], out=blocks[b0:b0 + step])
+
+
+def parity_check(H, L, yh, first_row, n, rows=1 << 16):
+    """max relative error of sampled row blocks of this rank's y = H x (host copy `yh`, rows
+    [first_row, first_row + yh.size)) against the oracle's fast path on the analytic x."""
+    import oracle
+    omsc, osub = oracle_problem(H, L)
+    S = min(rows, yh.size)
+    xs, ys = reserve(n, np.complex128), reserve(n, np.complex128)
+    nloc = yh.size
+    worst = 0.0
+    for first in sorted({first_row, first_row + ((nloc // 2 + 12345 * 2048) & ~(S - 1)) % nloc, first_row + nloc - S}):
+        for m in np.unique(omsc.masks):
+            wdw = (first ^ int(m)) & ~(S - 1)
+            xs[wdw:wdw + S] = host_x(wdw, S, n)
+        oracle.matmult_fast_range(omsc, osub, xs, ys, first // 2048, (first + S) // 2048, nthreads=os.cpu_count() or 1)
+        got = yh[first - first_row: first - first_row + S]
+        want = ys[first:first + S]
+        worst = max(worst, float(np.linalg.norm(got - want) / np.linalg.norm(want)))
+    return worst
+
+
 def time_region(lib, fn, steps, dist):
     """`steps` calls of fn between barriers, timed with CUDA events on the library stream."""
     ms = C.c_float()
@@ -398,6 +453,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end: host buffers in, host buffers out, copies inside the timed region ----
     e2e = None
+    parity = None
     host = []
     try:
         nbytes = nloc * 16
@@ -408,7 +464,8 @@ def run_ours(args, rank, world, local_rank):
         xh = np.ctypeslib.as_array(C.cast(host[0], C.POINTER(C.c_double)), shape=(2 * nloc,)).view(np.complex128)
         yh = np.ctypeslib.as_array(C.cast(host[1], C.POINTER(C.c_double)), shape=(2 * nloc,)).view(np.complex128)
         a, b = x.getOwnershipRange()
-        _capi.check(lib.dnm_vec_get_host(x.handle, 0, nloc, _capi.fp(xh)))
+        # host input with a closed form (checked against the oracle below): x[i] = base[i mod P] * w[i div P]
+        fill_host_x(xh, a, n)
 
         if world == 1:
             def e2e_step():
@@ -432,6 +489,13 @@ def run_ours(args, rank, world, local_rank):
             t = torch.tensor([e2e_sec], device='cuda', dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_sec = float(t.item())
+        # every rank checks sampled rows of its shard of y = H x against the oracle (1e-12, north star)
+        parity = parity_check(H, L, yh, a, n)
+        if dist is not None:
+            import torch
+            t = torch.tensor([parity], device='cuda', dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            parity = float(t.item())
         e2e = {'value': units * args.e2e_steps / e2e_sec, 'unit': UNIT, 'h2d_bytes_per_step': int(n * 16),
                'd2h_bytes_per_step': int(n * 16), 'steps': args.e2e_steps,
                'api': 'dnm_mat_mult_host (pinned host x -> H2D -> MatMult -> D2H -> pinned host y)'
@@ -486,6 +550,7 @@ def run_ours(args, rank, world, local_rank):
             'vs_baseline': None, 'dtype': 'c128 (f64 complex)', 'data': 'synthetic',
             'config': workload_config(args, L, world, H),
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+            'parity_rel_err_vs_oracle': parity,
             'extras': extras,
         }
         emit(out)

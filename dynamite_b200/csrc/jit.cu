@@ -169,6 +169,7 @@ struct Group {
   double c1, c2;
   bool imag, far;
   u64 farmask;
+  int peer;
 };
 
 // acc[r] += D_g(row) * x[row ^ mask_g] for every group of the pass.  `tile` = the staged tile,
@@ -190,7 +191,8 @@ void gen_groups(Out &o, const PassDesc &pd, const Geo &g_)
     G.c2 = S.cf[2 * g + 1];
     G.imag = (S.kp[g] & 1) != 0;
     G.farmask = S.far[g];
-    G.far = G.farmask != 0;
+    G.far = ((S.gd[g].w >> 17) & 1u) != 0;
+    G.peer = G.far ? (int)S.peer[g] : 0;
     if (G.c2 == 0.0) {  // one sign mask only
       G.sBw = 0;
       G.soB = 0;
@@ -223,7 +225,8 @@ void gen_groups(Out &o, const PassDesc &pd, const Geo &g_)
     const std::string e1 = expo(G.so1, s1t), eB = expo(G.soB, sBt);
     if (!e1.empty()) o("      const int e1 = %s;\n", e1.c_str());
     if (!eB.empty()) o("      const int eB = %s;\n", eB.c_str());
-    if (G.far) o("      const double2 *src = x + (base ^ 0x%llxll);\n", (u64)((i64)G.farmask & ~g_.rowbits));
+    if (G.far && G.peer) o("      const double2 *src = xs.p[%d] + (base ^ 0x%llxll);  // rank ^ %d over NVLink\n", G.peer, (u64)((i64)G.farmask & ~g_.rowbits), G.peer);
+    else if (G.far) o("      const double2 *src = x + (base ^ 0x%llxll);\n", (u64)((i64)G.farmask & ~g_.rowbits));
     else o("      const double2 *src = tile + (tid ^ 0x%xu);\n", lamlo);
     auto operand = [&](int r) -> std::string {
       char buf[128];
@@ -314,7 +317,8 @@ void gen_classic(Out &o, const PassDesc &pd, int index)
   o("// ---- pass %d (classic): T=%d R=%d, %d groups, %s, far_bits=%d\n", index, g.T, R, P.ngroups,
     P.accumulate ? "accumulate" : "write", P.far_bits);
   o("extern \"C\" __global__ void __launch_bounds__(%d, %d)\n", NT, minb);
-  o("dnm_jit_p%d(const double2 *__restrict__ x, double2 *__restrict__ y, const double *__restrict__ diag, i64 rank_bits)\n{\n",
+  o("dnm_jit_p%d(const double2 *__restrict__ x, double2 *__restrict__ y, const double *__restrict__ diag, i64 rank_bits,\n"
+    "           const __grid_constant__ Peers xs)\n{\n",
     index);
   o("  extern __shared__ double2 tile[];\n");
   o("  const u32 tid = threadIdx.x;\n");
@@ -423,7 +427,8 @@ void gen_pipelined(Out &o, const PassDesc &pd, int index)
 
   o("extern \"C\" __global__ void __launch_bounds__(%d, %d)\n", NT, ctas);
   o("dnm_jit_p%d(const __grid_constant__ TMap tmx, const __grid_constant__ TMap tmy, const double2 *__restrict__ x,\n"
-    "           double2 *__restrict__ y, const double *__restrict__ diag, i64 rank_bits, u64 ntiles)\n{\n",
+    "           double2 *__restrict__ y, const double *__restrict__ diag, i64 rank_bits, u64 ntiles,\n"
+    "           const __grid_constant__ Peers xs)\n{\n",
     index);
   o("  extern __shared__ __align__(1024) unsigned char smem[];\n");
   o("  double2 *ring = reinterpret_cast<double2 *>(smem);\n");
@@ -560,6 +565,7 @@ const char *PRELUDE =
     "// generated by dynamite_b200 (csrc/jit.cu): operator-specialised window-tiled MatMult passes\n"
     "typedef long long i64;\ntypedef unsigned long long u64;\ntypedef unsigned int u32;\n"
     "struct __align__(64) TMap { u64 opaque[16]; };\n"
+    "struct Peers { const double2 *p[16]; };  // the input vector on rank (this ^ h)\n"
     "__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }\n"
     "__device__ __forceinline__ void cpa16(void *s, const void *g)\n{\n"
     "  asm volatile(\"cp.async.cg.shared.global [%0], [%1], 16;\\n\" ::\"r\"(smem_u32(s)), \"l\"(g) : \"memory\");\n}\n"
@@ -720,19 +726,24 @@ const CUtensorMap *tensor_map(const Kernel &k, const void *ptr)
 }  // namespace
 
 void launch(const Kernel &k, unsigned long long ntiles, int sm_count, cudaStream_t stream, const cplx *x, cplx *y,
-            const double *diag, long long rank_bits, long long)
+            const double *diag, long long rank_bits, const cplx *const *peers)
 {
   CUresult rc;
+  struct {
+    const cplx *p[MAX_RANKS];
+  } xs;
+  for (int h = 0; h < MAX_RANKS; ++h) xs.p[h] = peers ? peers[h] : nullptr;
   if (k.pipelined) {
     static const CUtensorMap zero = {};
     const CUtensorMap *tmx = k.rank > 0 ? tensor_map(k, x) : &zero;
     const CUtensorMap *tmy = (k.rank > 0 && k.reduce) ? tensor_map(k, y) : &zero;
     const unsigned grid = (unsigned)std::min<unsigned long long>(ntiles, (unsigned long long)sm_count * k.ctas_per_sm);
-    void *args[] = {(void *)tmx, (void *)tmy, (void *)&x, (void *)&y, (void *)&diag, (void *)&rank_bits, (void *)&ntiles};
+    void *args[] = {(void *)tmx, (void *)tmy, (void *)&x, (void *)&y, (void *)&diag, (void *)&rank_bits, (void *)&ntiles,
+                    (void *)&xs};
     rc = driver().launchKernel((CUfunction)k.func, grid, 1, 1, (unsigned)k.threads, 1, 1, (unsigned)k.smem, (CUstream)stream, args,
                                nullptr);
   } else {
-    void *args[] = {(void *)&x, (void *)&y, (void *)&diag, (void *)&rank_bits};
+    void *args[] = {(void *)&x, (void *)&y, (void *)&diag, (void *)&rank_bits, (void *)&xs};
     rc = driver().launchKernel((CUfunction)k.func, (unsigned)ntiles, 1, 1, (unsigned)k.threads, 1, 1, (unsigned)k.smem,
                                (CUstream)stream, args, nullptr);
   }

@@ -74,8 +74,9 @@ Module *compile(const std::string &src, const std::vector<PassDesc> &passes, std
 // compile only (no GPU needed): cubin bytes, empty on failure
 std::vector<char> compile_cubin(const std::string &src, std::string &log);
 
+// peers[h] = mapping of the input vector on rank (this ^ h), for passes with folded remote masks
 void launch(const Kernel &k, unsigned long long ntiles, int sm_count, cudaStream_t stream, const cplx *x, cplx *y,
-            const double *diag, long long rank_bits, long long nloc_rows);
+            const double *diag, long long rank_bits, const cplx *const *peers);
 
 }  // namespace jit
 }  // namespace dnm

@@ -37,6 +37,8 @@ using namespace tiled;
 
 // stream the launch helpers below enqueue on (the side stream while remote passes are issued)
 cudaStream_t g_launch_stream = nullptr;
+// peer mappings of the current input vector, indexed by partner rank XOR (folded remote masks)
+const cplx *g_peers[MAX_RANKS] = {nullptr};
 inline cudaStream_t launch_stream() { return g_launch_stream ? g_launch_stream : G.stream; }
 
 // Plain gather for masks no window can hold, and for index spaces smaller
@@ -177,6 +179,7 @@ struct Pass {
   int nterms = 0;
   int nmasks = 0;
   int nfar = 0;      // masks served through the L2 window (FAR groups)
+  int nremote = 0;   // ... of which read another rank's shard (folded remote masks: generated kernels only)
   i64 wbits = 0;     // window bit positions
   std::vector<int> W;               // the same as a list: W[j] = index bit of window coordinate j
   const jit::Kernel *jk = nullptr;  // operator-specialised kernel of this pass (owned by TiledPlan::jit)
@@ -211,6 +214,8 @@ struct TiledPlan {
   size_t batch_stage_bytes = 0;   // shared memory for the largest staged term table among them
   int batch_T = 0, batch_R = 0;
   jit::Module *jit = nullptr;  // generated kernels of the lean passes
+  bool fold = false;           // remote masks are FAR groups of local passes (generated kernels only)
+  bool fold_failed = false;    // ... but no lean pass could take them: plan again without folding
   bool dma = false;          // remote shards are staged by the copy engines while the local passes run
   cplx *stage[2] = {nullptr, nullptr};
   cudaEvent_t ev_staged[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
@@ -463,10 +468,16 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
     return rp;
   };
   std::vector<unsigned long long> gfar;  // per group: the local flip mask of a FAR group, else 0
+  std::vector<u8> gisfar, gpeer;         // per group: FAR flag, partner rank xor (folded remote masks)
+  int nremote = 0;
   for (size_t mi = 0; mi < masks.size(); ++mi) {
     const NMask *nm = masks[mi];
     gfar.resize(lam.size(), 0);
+    gisfar.resize(lam.size(), 0);
+    gpeer.resize(lam.size(), 0);
     const bool is_far = mi >= masks.size() - nfar;
+    const int mpeer = (int)(nm->mask >> nloc);
+    if (is_far && mpeer) ++nremote;
     const u32 l = extract(nm->mask & lmask);
     if (allow_tables && getenv("DNM_NO_CTABLE") == nullptr) {
       // masks with real AND imaginary terms: one joint basis, one table of complex coefficients,
@@ -553,6 +564,8 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
           pat.push_back(0);
           kp.push_back((u8)(kind | (PATH_PAIR << 1)));
           gfar.push_back(is_far ? (unsigned long long)(nm->mask & lmask) : 0ull);
+          gisfar.push_back(is_far ? 1 : 0);
+          gpeer.push_back(is_far ? (u8)mpeer : 0);
           continue;
         }
       }
@@ -623,6 +636,8 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
   }
   DNM_REQUIRE(sw.size() < 65535, DNM_ERR_UNSUPPORTED, "too many terms in one pass (%zu)", sw.size());
   gfar.resize(lam.size(), 0);
+  gisfar.resize(lam.size(), 0);
+  gpeer.resize(lam.size(), 0);
 
   std::vector<i64> rowoff((size_t)1 << (T - B));
   for (size_t h = 0; h < rowoff.size(); ++h) {
@@ -684,6 +699,7 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
   ps.wbits = wbits;
   ps.W = W;
   ps.nfar = (int)nfar;
+  ps.nremote = nremote;
   // large passes stage csign/sw/rb (16 B per term) in shared memory when that still leaves two tiles per SM
   ps.p.staged = ((any_table || !(ps.p.ngroups <= SMALL_GROUPS && ps.nterms <= SMALL_TERMS)) && (size_t)ps.nterms * 16 <= 40 * 1024 &&
                  getenv("DNM_NO_STAGE") == nullptr) ? 1 : 0;
@@ -710,12 +726,13 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
       for (int g = 0; g < ps.p.ngroups; ++g) {
         ps.st.gd[g] = make_uint4(lam[g], sw[2 * g], sw[2 * g + 1],
                                  (rb[2 * g] & 0xffu) | ((rb[2 * g + 1] & 0xffu) << 8) | ((u32)(kp[g] & 1) << 16) |
-                                     (gfar[g] ? (1u << 17) : 0u));
+                                     (gisfar[g] ? (1u << 17) : 0u));
         ps.st.far[g] = gfar[g];
+        ps.st.peer[g] = gpeer[g];
       }
     if (lean && getenv("DNM_NO_CPLX") == nullptr)
       for (int g = 0; g + 1 < ps.p.ngroups; ++g) {
-        const bool plain_pair = (ps.st.gd[g].w & 0xffffu) == 0 && (ps.st.gd[g + 1].w & 0xffffu) == 0 && !gfar[g] && !gfar[g + 1];
+        const bool plain_pair = (ps.st.gd[g].w & 0xffffu) == 0 && (ps.st.gd[g + 1].w & 0xffffu) == 0 && !gisfar[g] && !gisfar[g + 1];
         if (lam[g] == lam[g + 1] && !(kp[g] & 1) && (kp[g + 1] & 1) && plain_pair) {
           ps.st.gd[g].x |= 0x80000000u;
           ++g;
@@ -742,8 +759,10 @@ bool pair_eligible(const NMask *nm)
   return true;
 }
 
+// `fold` (may be null): masks of the REMOTE groups to attach to the first lean pass of this (local)
+// group as FAR groups that read the partner's shard through its peer mapping; emptied when used.
 void plan_group(TiledPlan &plan, std::vector<const NMask *> remaining, int peer_xor, int T, int R, int B,
-                bool first_group, int verbose, int fmax = 0)
+                bool first_group, int verbose, int fmax = 0, std::vector<const NMask *> *fold = nullptr)
 {
   const int nloc = plan.nloc;
   const i64 lmask = ((i64)1 << nloc) - 1;
@@ -841,6 +860,21 @@ void plan_group(TiledPlan &plan, std::vector<const NMask *> remaining, int peer_
       ps = make_pass(chosen, Wpos, T, R, B, nloc, wrote ? 1 : 0);
     }
     for (size_t k = 0; k < remaining.size(); ++k) taken[k] = taken[k] || taken_far[k];
+    if (fold && !fold->empty() && chosen_ok && ps.small && ps.p.lean &&
+        (size_t)ps.p.ngroups + 2 * fold->size() <= (size_t)SMALL_GROUPS &&
+        (size_t)ps.nterms + 4 * fold->size() <= (size_t)SMALL_TERMS) {
+      std::vector<const NMask *> all3(chosen);
+      all3.insert(all3.end(), farm.begin(), farm.end());
+      all3.insert(all3.end(), fold->begin(), fold->end());
+      Pass folded = make_pass(all3, Wpos, T, R, B, nloc, wrote ? 1 : 0, farm.size() + fold->size(), F);
+      if (folded.small && folded.p.lean) {
+        for (void *q : ps.owned) cudaFree(q);
+        ps = std::move(folded);
+        fold->clear();
+      } else {
+        for (void *q : folded.owned) cudaFree(q);
+      }
+    }
     ps.peer_xor = peer_xor;
     if (verbose)
       fprintf(stderr, "[dnm] pass %zu: peer^%d window=0x%llx far=0x%llx masks=%d (%d far) terms=%d %s\n",
@@ -900,7 +934,7 @@ void launch_pass(const Pass &ps, const cplx *x, cplx *y, const double *diag, i64
 {
   if (ps.jk) {
     jit::launch(*ps.jk, (unsigned long long)ntiles, G.sm_count, launch_stream(), x, y, diag, (long long)ps.p.rank_bits,
-                (long long)ntiles << ps.T);
+                g_peers);
     count_launch();
     return;
   }
@@ -1036,7 +1070,7 @@ TiledPlan::Need stage_need(const std::vector<const NMask *> &masks, int nloc)
 
 // One candidate plan for a fixed tile size T and run length 2^B.
 std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &masks, int T, int R, int B, int fmax_in,
-                                     int verbose)
+                                     int verbose, bool allow_fold = false)
 {
   std::unique_ptr<TiledPlan> plan(new TiledPlan());
   const int n = ilog2(A->M);
@@ -1078,7 +1112,30 @@ std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &mas
     // local buffer while the SMs run the local passes; the group's passes then run on local memory).
     // DNM_REMOTE=peer keeps the in-kernel NVLink loads, DNM_REMOTE=peer_overlap runs them on a side stream.
     const char *rmode = getenv("DNM_REMOTE");
-    const std::string mode = rmode ? rmode : "dma";
+    std::string mode = rmode ? rmode : (allow_fold ? "fold" : "dma");
+    // fold: the remote masks join a local pass of generated code as FAR groups whose operand is the
+    // partner's shard, read over NVLink inside that pass -- no staging buffers, no extra
+    // read-modify-write sweep over y per remote group
+    std::vector<const NMask *> fold;
+    if (mode == "fold" && allow_fold && groups.size() > 1) {
+      for (auto it = groups.begin(); it != groups.end();) {
+        if (it->first == 0) {
+          ++it;
+          continue;
+        }
+        bool ok = true;
+        for (const NMask *nm : it->second) ok = ok && pair_eligible(nm);
+        if (ok) {
+          fold.insert(fold.end(), it->second.begin(), it->second.end());
+          it = groups.erase(it);
+        } else {
+          ++it;
+        }
+      }
+      plan->fold = !fold.empty();
+      if (plan->fold) plan->any_remote = true;
+    }
+    if (mode == "fold") mode = "dma";  // whatever could not be folded
     plan->dma = groups.size() > 1 && mode == "dma";
     plan->overlap = groups.size() > 1 && mode == "peer_overlap";
     bool first_local = true, first_remote = true;
@@ -1086,7 +1143,7 @@ std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &mas
     const int fmax = std::max(0, std::min(fmax_in, nloc - T));
     for (auto &kv : groups) {
       if (kv.first == 0) {
-        plan_group(*plan, kv.second, kv.first, T, R, B, first_local, verbose, fmax);
+        plan_group(*plan, kv.second, kv.first, T, R, B, first_local, verbose, fmax, &fold);
         first_local = false;
       } else {
         const size_t before = plan->passes.size(), dbefore = plan->directs.size();
@@ -1104,6 +1161,7 @@ std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &mas
         }
       }
     }
+    if (plan->fold && !fold.empty()) plan->fold_failed = true;  // no lean pass could take the remote masks
   }
   // cost in vector sweeps over HBM: a writing pass reads x and writes y (2), an
   // accumulating pass also re-reads y (3); a direct gather re-reads x once per mask.
@@ -1124,7 +1182,7 @@ std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &mas
   return plan;
 }
 
-TiledPlan *build_plan(dnm_mat_s *A)
+TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false)
 {
   const int n = ilog2(A->M);
   const int nloc = n - ilog2(G.nranks);
@@ -1166,7 +1224,9 @@ TiledPlan *build_plan(dnm_mat_s *A)
   std::unique_ptr<TiledPlan> best;
   Cand best_c{0, 0, 0, false};
   for (const Cand &c : candidates) {
-    std::unique_ptr<TiledPlan> cand = plan_with(A, masks, c.T, rows_for(c.T, A->tile_rows), c.B, c.f, A->verbose);
+    const bool fold_ok = jit_possible && G.nranks > 1 && !no_fold;
+    std::unique_ptr<TiledPlan> cand = plan_with(A, masks, c.T, rows_for(c.T, A->tile_rows), c.B, c.f, A->verbose, fold_ok);
+    if (cand->fold_failed) cand = plan_with(A, masks, c.T, rows_for(c.T, A->tile_rows), c.B, c.f, A->verbose, false);
     if (A->verbose)
       fprintf(stderr, "[dnm] plan T=%d B=%d far<=%d: %zu passes + %zu direct, cost %.2f sweeps\n", c.T, c.B, c.f,
               cand->passes.size(), cand->directs.size(), cand->cost);
@@ -1264,8 +1324,20 @@ TiledPlan *build_plan(dnm_mat_s *A)
         }
       }
       best->jit = jit::compile(src, descs, log);
+      if (!best->jit && best->fold && !no_fold) {
+        // folded remote masks only exist in generated code: plan again the classic way
+        if (A->verbose) fprintf(stderr, "[dnm] generated kernels unavailable (%s): planning without folded remote masks\n", log.c_str());
+        best.reset();
+        return build_plan(A, true);
+      }
       if (best->jit) {
         for (size_t k = 0; k < which.size(); ++k) best->passes[which[k]].jk = &best->jit->kernels[k];
+        bool stranded = false;  // a pass with folded remote masks that did not get a generated kernel
+        for (const Pass &ps : best->passes) stranded = stranded || (ps.nremote > 0 && !ps.jk);
+        if (stranded && !no_fold) {
+          best.reset();
+          return build_plan(A, true);
+        }
         if (A->verbose) fprintf(stderr, "[dnm] %zu generated kernels (%zu bytes of source)\n", which.size(), src.size());
       } else if (A->verbose || A->jit == 1) {
         fprintf(stderr, "[dnm] generated kernels unavailable, using the generic tiled kernel: %s\n", log.c_str());
@@ -1331,6 +1403,12 @@ void tiled_mult(dnm_mat_s *A, dnm_vec_t xv, dnm_vec_t yv)
   }
 
   if (plan.any_remote) stream_barrier();  // every rank's x is complete before anyone pulls from it
+  for (int h = 0; h < MAX_RANKS; ++h) g_peers[h] = nullptr;
+  if (plan.fold)
+    for (int h = 1; h < G.nranks; ++h) {
+      g_peers[h] = xv->peer[G.rank ^ h];
+      DNM_REQUIRE(g_peers[h] != nullptr, DNM_ERR_COMM, "input vector is not mapped on peer rank %d", G.rank ^ h);
+    }
 
   if (plan.dma && plan.any_remote) {
     const size_t bytes = sizeof(cplx) * (size_t)nloc_rows;

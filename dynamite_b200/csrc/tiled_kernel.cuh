@@ -107,6 +107,9 @@ struct SmallTables {
   // concurrently), not from the tile
   uint4 gd[SMALL_GROUPS];
   unsigned long long far[SMALL_GROUPS];
+  // FAR group whose operand lives on another rank (sharded vectors): x is read from rank ^ peer[g]
+  // through its peer mapping, inside the pass (generated kernels only)
+  unsigned char peer[SMALL_GROUPS];
 };
 
 constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v / 2); }

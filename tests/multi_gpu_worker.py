@@ -70,6 +70,23 @@ def main():
                 H.get_mat().set_option('tile_bits', 0)      # drops the cached plan
                 y2 = H.dot(x)
                 check(f'matmult[{mode}] {name} L={L}', rel_err(y2.vec[a:b], want[a:b]) < 1e-12)
+            # remote masks folded into the local passes of generated code (FAR groups reading the partner's
+            # shard over NVLink inside the pass): forced on at this small size, several tile shapes
+            os.environ['DNM_REMOTE'] = 'fold'
+            mat = H.get_mat()
+            mat.set_option('jit', 1)
+            for tile_bits, far in ((0, -1), (9, 3), (10, 0), (11, 2)):
+                mat.set_option('tile_bits', tile_bits)
+                mat.set_option('far_bits', far)
+                y5 = H.dot(x)
+                check(f'matmult[fold T={tile_bits} far={far}] {name} L={L} diag={diag}',
+                      rel_err(y5.vec[a:b], want[a:b]) < 1e-12, f'err={rel_err(y5.vec[a:b], want[a:b]):.2e}')
+                if name != 'SYK' and (diag or name == 'XX'):
+                    check(f'generated kernels ran [{name}]', mat.get_info('jit_passes') >= 1)
+            mat.set_option('jit', -1)
+            mat.set_option('far_bits', -1)
+            os.environ.pop('DNM_REMOTE', None)
+            mat.set_option('tile_bits', 0)
             # DMA staging copies only the part of a partner shard this rank can touch (XX+YY terms:
             # half of it or nothing); the rest of the staging buffer is poisoned with NaNs here
             os.environ['DNM_POISON_STAGE'] = '1'
