@@ -313,6 +313,21 @@ def parity_check(H, L, yh, first_row, n, rows=1 << 16):
     return worst
 
 
+def nvlink_kib(index):
+    """(tx, rx) KiB counters of one GPU summed over its NVLink links (`nvidia-smi nvlink -gt d`), or None"""
+    import re
+    try:
+        txt = subprocess.run(['nvidia-smi', 'nvlink', '-gt', 'd', '-i', str(index)], capture_output=True, text=True,
+                             timeout=20).stdout
+    except (OSError, subprocess.SubprocessError):
+        return None
+    tx = [int(v) for v in re.findall(r'Data Tx:\s*(\d+)\s*KiB', txt)]
+    rx = [int(v) for v in re.findall(r'Data Rx:\s*(\d+)\s*KiB', txt)]
+    if not tx and not rx:
+        return None
+    return sum(tx), sum(rx)
+
+
 def time_region(lib, fn, steps, dist):
     """`steps` calls of fn between barriers, timed with CUDA events on the library stream."""
     ms = C.c_float()
@@ -329,67 +344,129 @@ def time_region(lib, fn, steps, dist):
     return ms.value / 1e3
 
 
-def run_extras(level, world, lib):
-    """evolve / eigsolve wall seconds on the other BASELINE configs (single GPU)."""
+def run_extras(level, world, lib, args, L_main):
+    """evolve / eigsolve wall seconds (and a few more timings) on the other BASELINE configs.
+    N = 1: C1, C2, C4, an rdm and the C3 evolve.  N > 1: the same calls on SHARDED vectors (evolve on
+    the bench Hamiltonian at L = 30 + log2 N, a Full-space eigsolve at 2^26 rows per GPU) and, at
+    N = 8, BASELINE C5 (L = 33 long_range: MatMult, sampled-row parity, evolve)."""
+    from dynamite_b200.computations import reduced_density_matrix
     from dynamite_b200.hamiltonians import build_hamiltonian
     from dynamite_b200.states import State
     from dynamite_b200.subspaces import Full, Parity, SpinConserve
     out = {}
-    if world != 1 or level == 'none':
+    if level == 'none':
         return out
 
-    def timed(fn):
+    def timed(fn, warm=True):
         # the first call also pays CUDA's lazy loading of every kernel variant; report the repeat
-        fn()
+        if warm:
+            fn()
         lib.dnm_synchronize()
         t0 = time.perf_counter()
         r = fn()
         lib.dnm_synchronize()
         return time.perf_counter() - t0, r
 
-    # C1: L=20 Heisenberg, Full, evolve t=1 (--no_normalize_t)
-    H = build_hamiltonian('heisenberg', 20)
-    H.subspace = Full(L=20)
-    s = State(L=20, subspace=H.subspace)
-    s.vec.setRandom(1)
-    s.vec.normalize()
-    s.set_initialized()
-    H.get_mat()
-    dt, _ = timed(lambda: H.evolve(s, 1.0))
-    out['C1_L20_heisenberg_evolve_t1_s'] = dt
-    H.destroy_mat()
-    # C2: L=26 Heisenberg (XXZ Delta=1), SpinConserve k=13, lowest 4 eigenpairs
-    H = build_hamiltonian('heisenberg', 26)
-    H.subspace = SpinConserve(26, 13)
-    H.get_mat()
-    dt, ev = timed(lambda: H.eigsolve(nev=4))
-    out['C2_L26_spinconserve_eigsolve_nev4_s'] = dt
-    out['C2_lowest_eigenvalue'] = float(ev[0])
-    H.destroy_mat()
-    if level == 'full':
-        # C3: L=30 MBL evolve, t = 50/||H||_inf (benchmark.py defaults); ncv is capped by HBM
-        H = build_hamiltonian('MBL', 30)
-        H.subspace = Full(L=30)
-        s = State(L=30, subspace=H.subspace)
+    def random_state(L, sub):
+        s = State(L=L, subspace=sub)
         s.vec.setRandom(1)
         s.vec.normalize()
         s.set_initialized()
-        nrm = H.infinity_norm()
-        r = State(L=30, subspace=H.subspace)
-        dt, _ = timed(lambda: H.evolve(s, 50.0 / nrm, result=r))
-        out['C3_L30_MBL_evolve_t50_over_norm_s'] = dt
+        return s
+
+    def mult_ms(H, s, reps):
+        mat = H.get_mat()
+        r = State(subspace=s.subspace)
+        for _ in range(3):
+            mat.mult(s.vec, r.vec)
+        ms = C.c_float()
+        lib.dnm_synchronize()
+        lib.dnm_timer_start()
+        for _ in range(reps):
+            mat.mult(s.vec, r.vec)
+        lib.dnm_timer_stop(C.byref(ms))
+        return ms.value / reps, mat, r
+
+    if world == 1:
+        # C1: L=20 Heisenberg, Full, evolve t=1 (--no_normalize_t)
+        H = build_hamiltonian('heisenberg', 20)
+        H.subspace = Full(L=20)
+        s = random_state(20, H.subspace)
+        H.get_mat()
+        dt, _ = timed(lambda: H.evolve(s, 1.0))
+        out['C1_L20_heisenberg_evolve_t1_s'] = dt
         H.destroy_mat()
-        del s, r
-        # C4: SYK N=40 Majoranas, Parity, evolve
+        # C2: L=26 Heisenberg (XXZ Delta=1), SpinConserve k=13, lowest 4 eigenpairs
+        H = build_hamiltonian('heisenberg', 26)
+        H.subspace = SpinConserve(26, 13)
+        H.get_mat()
+        dt, ev = timed(lambda: H.eigsolve(nev=4))
+        out['C2_L26_spinconserve_eigsolve_nev4_s'] = dt
+        out['C2_lowest_eigenvalue'] = float(ev[0])
+        H.destroy_mat()
+        # C4: SYK N=40 Majoranas, Parity: MatMult (8 MiB vector: L2-resident, issue-bound -- the HBM model
+        # number is reported for completeness only) and evolve
         H = build_hamiltonian('SYK', 20)
         H.subspace = Parity('even', L=20)
-        s = State(L=20, subspace=H.subspace)
-        s.vec.setRandom(1)
-        s.vec.normalize()
-        s.set_initialized()
+        s = random_state(20, H.subspace)
+        ms, mat, r = mult_ms(H, s, 20)
+        out['C4_SYK40_parity_matmult_ms'] = ms
+        out['C4_SYK40_model_gbs'] = mat.get_info('model_bytes') / (ms * 1e-3) / 1e9
+        out['C4_note'] = 'vector is L2-resident (8 MiB): bound by instruction issue / L2, not HBM'
         nrm = H.infinity_norm()
         dt, _ = timed(lambda: H.evolve(s, 50.0 / nrm))
         out['C4_SYK40_parity_evolve_t50_over_norm_s'] = dt
+        H.destroy_mat()
+        del s, r
+        # rdm: L=24 random state, keep = the first half of the chain (benchmark.py:293-296)
+        s = random_state(24, Full(L=24))
+        dt, _ = timed(lambda: reduced_density_matrix(s, list(range(12))))
+        out['rdm_L24_keep12_s'] = dt
+        del s
+        if level in ('quick', 'full'):
+            # C3: L=30 MBL evolve, t = 50/||H||_inf (benchmark.py defaults); ncv is capped by HBM
+            H = build_hamiltonian('MBL', 30)
+            H.subspace = Full(L=30)
+            s = random_state(30, H.subspace)
+            nrm = H.infinity_norm()
+            r = State(L=30, subspace=H.subspace)
+            dt, _ = timed(lambda: H.evolve(s, 50.0 / nrm, result=r), warm=False)
+            out['C3_L30_MBL_evolve_t50_over_norm_s'] = dt
+            H.destroy_mat()
+            del s, r
+        return out
+
+    # ---- sharded extras -------------------------------------------------------------------
+    p = int(round(math.log2(world)))
+    H = build_hamiltonian(args.H, L_main)
+    H.subspace = Full(L=L_main)
+    s = random_state(L_main, H.subspace)
+    nrm = H.infinity_norm()
+    r = State(L=L_main, subspace=H.subspace)
+    dt, _ = timed(lambda: H.evolve(s, 10.0 / nrm, result=r), warm=False)
+    out[f'sharded_L{L_main}_{args.H}_evolve_t10_over_norm_s'] = dt
+    H.destroy_mat()
+    del s, r
+    Le = 26 + p
+    H = build_hamiltonian('heisenberg', Le)
+    H.subspace = Full(L=Le)
+    H.get_mat()
+    dt, ev = timed(lambda: H.eigsolve(nev=4), warm=False)
+    out[f'sharded_L{Le}_heisenberg_full_eigsolve_nev4_s'] = dt
+    out[f'sharded_L{Le}_lowest_eigenvalue'] = float(ev[0])
+    H.destroy_mat()
+    if world == 8 and args.H != 'long_range':
+        # BASELINE C5: L=33 long-range model, Full space, 8 GPUs
+        L5 = 33
+        H = build_hamiltonian('long_range', L5)
+        H.subspace = Full(L=L5)
+        s = random_state(L5, H.subspace)
+        ms, mat, r = mult_ms(H, s, 5)
+        out['C5_L33_long_range_matmult_ms'] = ms
+        out['C5_unit_matmults_per_s'] = (1 << (L5 - 30)) / (ms * 1e-3)
+        nrm = H.infinity_norm()
+        dt, _ = timed(lambda: H.evolve(s, 10.0 / nrm, result=r), warm=False)
+        out['C5_L33_long_range_evolve_t10_over_norm_s'] = dt
         H.destroy_mat()
     return out
 
@@ -439,14 +516,25 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     lib.dnm_launch_count(1)
+    nv0 = nvlink_kib(local_rank) if world > 1 else None
     sec = time_region(lib, step, args.steps, dist)
+    nv1 = nvlink_kib(local_rank) if world > 1 else None
     launches = int(lib.dnm_launch_count(0))
+    nvlink = None
+    if nv0 and nv1:
+        # NVLink volume of this rank per MatMult (the counters tick in KiB); max over ranks below
+        nvlink = [(nv1[0] - nv0[0]) * 1024.0 / args.steps, (nv1[1] - nv0[1]) * 1024.0 / args.steps]
     clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
         import torch
         t = torch.tensor([sec], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec = float(t.item())
+    if dist is not None:
+        import torch
+        t = torch.tensor(nvlink if nvlink else [-1.0, -1.0], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nvlink = [float(v) for v in t.tolist()] if t[1].item() >= 0 else None
     units = n / ROWS_UNIT
     value = units * args.steps / sec
     ms_per_step = sec / args.steps * 1e3
@@ -541,7 +629,7 @@ def run_ours(args, rank, world, local_rank):
     y.destroy()
     H.destroy_mat()
 
-    extras = run_extras(args.extras, world, lib) if rank == 0 or world > 1 else {}
+    extras = run_extras(args.extras, world, lib, args, L) if rank == 0 or world > 1 else {}
 
     if rank == 0:
         out = {
@@ -551,6 +639,7 @@ def run_ours(args, rank, world, local_rank):
             'config': workload_config(args, L, world, H),
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
             'parity_rel_err_vs_oracle': parity,
+            'nvlink_bytes_per_matmult_max_rank': ({'tx': nvlink[0], 'rx': nvlink[1]} if nvlink else None),
             'extras': extras,
         }
         emit(out)

@@ -97,6 +97,7 @@ def eigsolve(H, getvecs=False, nev=1, which='lowest', target=None, tol=None, sub
         raise ValueError(f'invalid value "{which}" for parameter "which"') from None
     eps.setTolerances(tol=tol, max_it=max_its)
     eps.setFromOptions()
+    eps.keep_vectors = bool(getvecs)
     eps.solve()
     nconv = eps.getConverged()
     reason = eps.getConvergedReason()
@@ -127,7 +128,8 @@ def eigsolve(H, getvecs=False, nev=1, which='lowest', target=None, tol=None, sub
 
 def reduced_density_matrix(state, keep):
     """Trace out every spin not in ``keep`` (reference ``computations.py:294-350``).
-    Computed on the device; the matrix is returned on every rank."""
+    Computed on the device.  As in the reference the matrix is returned on rank 0 and every other
+    rank gets the 1x1 matrix [[-1]]; an empty ``keep`` gives [[1]]."""
     if not state.subspace.product_state_basis:
         raise ValueError('reduced density matrices only supported for product state subspaces')
     keep = np.array(keep, dtype=dnm_int_t).reshape(-1)
@@ -138,8 +140,14 @@ def reduced_density_matrix(state, keep):
         raise ValueError('values in keep must be between 0 and L-1')
     if np.any(np.diff(keep) <= 0):
         raise ValueError('keep array must be strictly increasing')
+    if keep.size == 0:
+        return np.array([[1]], dtype=np.complex128)
     from ._backend import bpetsc
-    return bpetsc.reduced_density_matrix(state.vec, state.subspace._to_c(), keep)
+    from .petsc import COMM_WORLD
+    dm = bpetsc.reduced_density_matrix(state.vec, state.subspace._to_c(), keep)
+    if COMM_WORLD.size > 1 and COMM_WORLD.rank != 0:
+        return np.array([[-1]], dtype=np.complex128)
+    return dm
 
 
 def entanglement_entropy(state, keep):

@@ -79,6 +79,29 @@ __global__ void k_col_second(const double *__restrict__ d_h2, int nh, const doub
 
 __global__ void k_sqrt_inplace(double *v) { *v = sqrt(*v); }
 
+// Lanczos column j of a Hermitian operator: h = (<v_{j-1}, w>, <v_j, w>) (only <v_0, w> when j = 0),
+// sq = ||w - h.V||^2.  Writes the tridiagonal column, the scale factor and the breakdown flag.
+__global__ void k_lanczos_col(const double *__restrict__ d_h, int j, const double *__restrict__ d_sq,
+                              double *__restrict__ Hcol, double *__restrict__ d_norm, double *__restrict__ d_lindep)
+{
+  const int nh = j == 0 ? 1 : 2;
+  double hh = 0.0;
+  for (int i = 0; i < nh; ++i) {
+    const int row = j + 1 - nh + i;
+    Hcol[2 * row] = d_h[2 * i];
+    Hcol[2 * row + 1] = d_h[2 * i + 1];
+    hh += d_h[2 * i] * d_h[2 * i] + d_h[2 * i + 1] * d_h[2 * i + 1];
+  }
+  const double sq = *d_sq;
+  const double nrm = sqrt(sq);
+  // invariant subspace: what is left of A v_j is rounding noise of its components along the basis
+  const double lindep = (!(nrm > 0.0) || sq <= 1e-28 * (sq + hh)) ? 1.0 : 0.0;
+  Hcol[2 * (j + 1)] = nrm;  // H[j+1, j]
+  Hcol[2 * (j + 1) + 1] = 0.0;
+  *d_lindep = lindep;
+  *d_norm = (lindep != 0.0) ? 0.0 : nrm;
+}
+
 // V[:, first : first+nout] <- V[:, first : first+nin] * Q   (Q real, nin x nout, column-major)
 // in place: every row block is staged in shared memory before anything is written.
 constexpr int ROT_ROWS = 64;
@@ -178,13 +201,44 @@ void arnoldi_column(dnm_mat_t A, Basis &B, int j, double *d_H, int ld, double *d
   vec_scale_dev(w, B.nloc, S.norm, true);
 }
 
+// One Lanczos column (Hermitian A, which dnm_mat_create guarantees): the three-term recurrence with
+// the two coefficients taken as computed inner products (local re-orthogonalisation against
+// v[j-1] and v[j]) -- 2 basis vectors per dot / axpy instead of j+1, the same H (tridiagonal) layout.
+void lanczos_column(dnm_mat_t A, Basis &B, int j, double *d_H, int ld, double *d_lindep, const ColScratch &S)
+{
+  int rc = dnm_mat_mult(A, B.v[j], B.v[j + 1]);
+  if (rc) throw Fail{rc};
+  cplx *w = B.ptr(j + 1);
+  double *Hcol = d_H + 2 * (size_t)ld * j;
+  VecList vs;
+  vs.n = 0;
+  if (j > 0) vs.p[vs.n++] = B.ptr(j - 1);
+  vs.p[vs.n++] = B.ptr(j);
+  multi_dot_dev(vs, w, B.nloc, S.h);
+  multi_axpy_sub_dev(vs, w, B.nloc, S.h, S.sq);
+  k_lanczos_col<<<1, 1, 0, G.stream>>>(S.h, j, S.sq, Hcol, S.norm, d_lindep + j);
+  count_launch();
+  DNM_CHECK_CUDA(cudaGetLastError());
+  vec_scale_dev(w, B.nloc, S.norm, true);
+}
+
 int64_t vector_budget(int64_t local_n, int64_t global_n)
 {
   size_t f = 0, t = 0;
   DNM_CHECK_CUDA(cudaMemGetInfo(&f, &t));
   const int64_t reserve = (int64_t)512 << 20;
   // workspace already parked in the pool counts as available
-  return std::max<int64_t>(0, ((int64_t)f - reserve) / (int64_t)(sizeof(cplx) * local_n)) + pool_count(global_n);
+  int64_t fit = std::max<int64_t>(0, ((int64_t)f - reserve) / (int64_t)(sizeof(cplx) * local_n)) + pool_count(global_n);
+  if (G.nranks > 1) {
+    // every rank must derive the same Krylov dimension (the same number of MatMults, reductions and
+    // collective vector creations): agree on the smallest budget
+    double v = -(double)fit;
+    DNM_CHECK_CUDA(cudaMemcpyAsync(G.d_scratch, &v, sizeof(double), cudaMemcpyHostToDevice, G.stream));
+    allreduce_max_dev(G.d_scratch, 1);
+    fetch_doubles(G.d_scratch, &v, 1);
+    fit = (int64_t)(-v);
+  }
+  return fit;
 }
 
 // wall-clock phase accounting, printed when DNM_TRACE is set
@@ -244,6 +298,8 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
   if (m + 1 > fit) {
     DNM_REQUIRE(fit >= 3, DNM_ERR_MEM, "not enough device memory for a Krylov basis (room for %lld vectors)",
                 (long long)fit);
+    if (G.rank == 0 && getenv("DNM_QUIET") == nullptr)
+      fprintf(stderr, "[dynamite_b200] evolve: Krylov dimension reduced from %d to %d to fit device memory\n", m, (int)fit - 1);
     m = (int)fit - 1;
   }
   DNM_REQUIRE(m >= 1, DNM_ERR_ARG, "Krylov dimension must be at least 1");
@@ -278,6 +334,7 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
   const size_t hbytes = sizeof(double) * (2 * (size_t)ld * ld + ld);
   std::vector<double> h_H(2 * (size_t)ld * ld + ld);
   const ColScratch S = col_scratch(ld);
+  DNM_REQUIRE(4096 + hbytes / sizeof(double) <= (size_t)SCRATCH_DOUBLES, DNM_ERR_ARG, "ncv=%d is too large", m);
 
   double anorm = 0;
   {
@@ -308,6 +365,26 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
   double t_new = round2((1.0 / anorm) * std::pow((fact * tol) / (4.0 * beta * anorm), xm));
   double t_now = 0.0;
 
+  // Hermitian operator: Lanczos recurrence (DNM_EVOLVE_ORTH=full keeps the Arnoldi column with full
+  // classical Gram-Schmidt + DGKS refinement)
+  const char *orth_env = getenv("DNM_EVOLVE_ORTH");
+  const bool lanczos = !(orth_env && !strcmp(orth_env, "full"));
+  bool use_graph = G.nranks == 1 && nloc <= ((int64_t)1 << 24) && getenv("DNM_NO_GRAPH") == nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  bool graph_failed = false;
+  struct GraphGuard {
+    cudaGraphExec_t &g;
+    ~GraphGuard()
+    {
+      if (g) cudaGraphExecDestroy(g);
+    }
+  } graph_guard{graph_exec};
+  if (use_graph) {
+    // the plan (and any generated kernels) must exist before a capture starts
+    int rc = dnm_mat_mult(A, B.v[0], B.v[1]);
+    if (rc) return rc;
+  }
+
   trace.mark(0);
   while (reason == 0) {
     ++its;
@@ -316,22 +393,53 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
 
     // v[0] = w / beta  (w lives in v[0])
     vec_scale(B.ptr(0), nloc, make_double2(1.0 / beta, 0.0));
-    DNM_CHECK_CUDA(cudaMemsetAsync(d_H, 0, hbytes, G.stream));
-    for (int j = 0; j < m; ++j) {
-      arnoldi_column(A, B, j, d_H, ld, d_lindep, S);
-      ++matmults;
-    }
-    // probe vector A*v[m] for the error estimate (harmless if the basis broke down earlier)
-    {
+    auto build_basis = [&]() {
+      DNM_CHECK_CUDA(cudaMemsetAsync(d_H, 0, hbytes, G.stream));
+      for (int j = 0; j < m; ++j) {
+        if (lanczos) lanczos_column(A, B, j, d_H, ld, d_lindep, S);
+        else arnoldi_column(A, B, j, d_H, ld, d_lindep, S);
+      }
+      // probe vector A*v[m] for the error estimate (harmless if the basis broke down earlier)
       int rc = dnm_mat_mult(A, B.v[m], B.v[m + 1]);
-      if (rc) return rc;
-      ++matmults;
+      if (rc) throw Fail{rc};
       vec_sqnorm_dev(B.ptr(m + 1), nloc, S.sq);
+      // pinned staging (pageable targets cannot be captured); the front of h_scratch belongs to fetch_doubles
+      DNM_CHECK_CUDA(cudaMemcpyAsync(G.h_scratch + 4096, d_H, hbytes, cudaMemcpyDeviceToHost, G.stream));
+    };
+    // Small problems are launch-bound (C1: 0.36 ms per column against a 0.027 ms MatMult): the whole
+    // basis construction of a sub-step is a fixed launch sequence, captured once as a CUDA graph
+    if (use_graph && !graph_exec && !graph_failed) {
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(G.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        bool ok = true;
+        try {
+          build_basis();
+        } catch (...) {
+          ok = false;
+        }
+        if (cudaStreamEndCapture(G.stream, &graph) != cudaSuccess || !ok || !graph) ok = false;
+        if (ok && cudaGraphInstantiate(&graph_exec, graph, 0) != cudaSuccess) ok = false;
+        if (graph) cudaGraphDestroy(graph);
+        if (!ok) {
+          cudaGetLastError();
+          graph_exec = nullptr;
+          graph_failed = true;
+        }
+      } else {
+        cudaGetLastError();
+        graph_failed = true;
+      }
     }
-    DNM_CHECK_CUDA(cudaMemcpyAsync(h_H.data(), d_H, hbytes, cudaMemcpyDeviceToHost, G.stream));
+    if (graph_exec) {
+      DNM_CHECK_CUDA(cudaGraphLaunch(graph_exec, G.stream));
+    } else {
+      build_basis();
+    }
+    matmults += m + 1;
     double avnorm2 = 0;
     trace.mark(1);
     fetch_doubles(S.sq, &avnorm2, 1);  // also synchronises the copy above
+    std::copy(G.h_scratch + 4096, G.h_scratch + 4096 + hbytes / sizeof(double), h_H.begin());
     trace.mark(2);
     const double avnorm = std::sqrt(avnorm2);
 
@@ -442,6 +550,8 @@ extern "C" int dnm_eigsolve(dnm_mat_t A, int nev, int which, double tol, int max
   if (ncv + 1 > fit) {
     DNM_REQUIRE(fit >= nev + 3, DNM_ERR_MEM, "not enough device memory for the Lanczos basis (room for %lld vectors)",
                 (long long)fit);
+    if (G.rank == 0 && getenv("DNM_QUIET") == nullptr)
+      fprintf(stderr, "[dynamite_b200] eigsolve: ncv reduced from %d to %d to fit device memory\n", ncv, (int)fit - 1);
     ncv = (int)fit - 1;
   }
   DNM_REQUIRE(ncv >= nev && ncv <= 512, DNM_ERR_ARG, "bad ncv=%d for nev=%d", ncv, nev);

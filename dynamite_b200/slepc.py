@@ -173,8 +173,15 @@ class EPS:
             v.destroy()
         # room for a few more pairs than requested: more may converge together
         cap = self.nev + 8
-        self._evecs = [Vec(m) for _ in range(cap)]
-        handles = (C.c_void_p * cap)(*[v.handle for v in self._evecs])
+        # eigenvector storage only when somebody will ask for vectors (EPS.keep_vectors, set by
+        # computations.eigsolve from its getvecs argument): at L=30 nine unused 16 GiB vectors would
+        # otherwise eat the memory the Lanczos basis needs
+        if getattr(self, 'keep_vectors', True):
+            self._evecs = [Vec(m) for _ in range(cap)]
+            handles = (C.c_void_p * cap)(*[v.handle for v in self._evecs])
+        else:
+            self._evecs = []
+            handles = None
         evals = np.zeros(cap, dtype=np.float64)
         errest = np.zeros(cap, dtype=np.float64)
         nconv, reason, its, mm = C.c_int(), C.c_int(), C.c_int(), C.c_int()
@@ -185,7 +192,7 @@ class EPS:
         self._evals, self._errest = evals, errest
 
     def getConverged(self):
-        return min(self.nconv, len(self._evecs))
+        return min(self.nconv, len(self._evals))
 
     def getConvergedReason(self):
         return self.reason
@@ -197,6 +204,8 @@ class EPS:
         if not 0 <= i < self.getConverged():
             raise IndexError('eigenpair index out of range')
         if vr is not None:
+            if not self._evecs:
+                raise RuntimeError('eigenvectors were not kept (EPS.keep_vectors = False)')
             self._evecs[i].copy(vr)
         return complex(self._evals[i], 0.0)
 

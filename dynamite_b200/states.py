@@ -14,6 +14,20 @@ class UninitializedError(RuntimeError):
     pass
 
 
+import pickle as _pickle
+
+
+class _SubspaceUnpickler(_pickle.Unpickler):
+    """Metadata written by the reference names ``dynamite.subspaces.<Class>``; files written here name
+    ``dynamite_b200.subspaces.<Class>``.  Both resolve to this package's classes."""
+
+    def find_class(self, module, name):
+        if module in ('dynamite.subspaces', 'dynamite_b200.subspaces'):
+            from . import subspaces
+            return getattr(subspaces, name)
+        return super().find_class(module, name)
+
+
 class State:
     def __init__(self, state=None, subspace=None, L=None, seed=None):
         self._vec = None
@@ -171,39 +185,68 @@ class State:
     # ---- checkpoint / resume ---------------------------------------------------------
     _VEC_CLASSID = 1211214   # PETSc VEC_FILE_CLASSID
 
-    def save(self, fname):
-        """``<fname>.vec`` in PETSc's binary Vec layout (big-endian int64 class id and length --
-        the 64-bit-index build the reference needs for L > 31 -- then interleaved complex128) and
-        ``<fname>.metadata`` = the pickled subspace, as reference ``states.py:627-652``.
-        Single-rank for now: rank r would write its block at offset 16 + 16*local_start."""
+    def save(self, fname, indices=None):
+        """``<fname>.vec`` in PETSc's binary Vec layout -- class id and length as big-endian PetscInt,
+        then interleaved big-endian complex128 -- and ``<fname>.metadata`` = the pickled subspace, as
+        reference ``states.py:627-652``.  ``indices`` = 32 or 64 selects the PetscInt width of the
+        header; by default 32 bits (what a default PETSc build, and the reference's own
+        ``petsc_config/complex-opt.py``, reads and writes) unless the length needs 64.
+        Multi-rank: rank 0 writes the metadata and the header, every rank its own block."""
         import pickle
         self.assert_initialized()
-        if COMM_WORLD.size != 1:
-            raise NotImplementedError('State.save is single-rank in this backend')
-        with open(fname + '.metadata', 'wb') as f:
-            pickle.dump(self.subspace, f)
         n = len(self)
-        with open(fname + '.vec', 'wb') as f:
-            f.write(np.array([self._VEC_CLASSID, n], dtype='>i8').tobytes())
+        if indices is None:
+            indices = 32 if n < 2**31 else 64
+        if indices not in (32, 64) or (indices == 32 and n >= 2**31):
+            raise ValueError('indices must be 32 or 64 (and 64 for vectors of 2^31 entries or more)')
+        hdr = np.array([self._VEC_CLASSID, n], dtype='>i4' if indices == 32 else '>i8').tobytes()
+        rank = COMM_WORLD.rank
+        if rank == 0:
+            with open(fname + '.metadata', 'wb') as f:
+                pickle.dump(self.subspace, f)
+            with open(fname + '.vec', 'wb') as f:
+                f.write(hdr)
+                f.truncate(len(hdr) + 16 * n)
+        if COMM_WORLD.size > 1:
+            COMM_WORLD.barrier()
+        first, last = self.vec.getOwnershipRange()
+        with open(fname + '.vec', 'r+b') as f:
+            f.seek(len(hdr) + 16 * first)
             block = 1 << 22
-            for a in range(0, n, block):
-                b = min(n, a + block)
+            for a in range(first, last, block):
+                b = min(last, a + block)
                 f.write(self.vec[a:b].astype('>c16').tobytes())
+        if COMM_WORLD.size > 1:
+            COMM_WORLD.barrier()
 
     @classmethod
     def from_file(cls, fname):
-        """inverse of :meth:`save` (uses ``pickle``: do not load untrusted files)"""
+        """inverse of :meth:`save` (uses ``pickle``: do not load untrusted files).  Accepts headers
+        written with 32-bit or 64-bit PetscInt; every rank reads its own block."""
         import pickle
         with open(fname + '.metadata', 'rb') as f:
-            subspace = pickle.load(f)
+            subspace = _SubspaceUnpickler(f).load()
         with open(fname + '.vec', 'rb') as f:
-            classid, n = np.frombuffer(f.read(16), dtype='>i8')
-            if classid != cls._VEC_CLASSID or subspace.get_dimension() != n:
+            head = f.read(4)
+            if len(head) == 4 and int(np.frombuffer(head, dtype='>i4')[0]) == cls._VEC_CLASSID:
+                n = int(np.frombuffer(f.read(4), dtype='>i4')[0])
+                hlen = 8
+            else:
+                rest = f.read(12)
+                if len(rest) != 12:
+                    raise RuntimeError('corrupt data encountered when loading state from file')
+                classid, n = (int(v) for v in np.frombuffer(head + rest, dtype='>i8'))
+                hlen = 16
+                if classid != cls._VEC_CLASSID:
+                    raise RuntimeError('corrupt data encountered when loading state from file')
+            if subspace.get_dimension() != n:
                 raise RuntimeError('corrupt data encountered when loading state from file')
             rtn = cls(subspace=subspace)
+            first, last = rtn.vec.getOwnershipRange()
+            f.seek(hlen + 16 * first)
             block = 1 << 22
-            for a in range(0, n, block):
-                b = min(n, a + block)
+            for a in range(first, last, block):
+                b = min(last, a + block)
                 rtn.vec[a:b] = np.frombuffer(f.read(16 * (b - a)), dtype='>c16').astype(np.complex128)
         rtn.set_initialized()
         return rtn

@@ -209,8 +209,10 @@ def test_rdm_kats_and_oracle(gpu):
     for keep, key in (([0, 2], 'rdm_L4_keep02_entropy'), ([1, 3], 'rdm_L4_keep13_entropy')):
         assert abs(entanglement_entropy(s, keep) - k[key]) < 2e-5
     full4 = oracle.Subspace({'type': 'full', 'L': 4})
-    for keep in ([], [0], [3], [0, 1], [1, 2, 3], [0, 1, 2, 3]):
+    for keep in ([0], [3], [0, 1], [1, 2, 3], [0, 1, 2, 3]):
         assert np.allclose(reduced_density_matrix(s, keep), oracle.rdm(psi, full4, keep), atol=1e-14)
+    # an empty keep never reaches the backend in the reference (computations.py:331-332)
+    assert np.array_equal(reduced_density_matrix(s, []), np.array([[1]], dtype=np.complex128))
     cs = k['rdm_complex_sign']
     s2 = State(L=2)
     s2.vec[0:4] = np.array([complex(*v) for v in cs['state']])
@@ -263,6 +265,26 @@ def test_state_api_and_checkpoint(gpu, tmp_path):
     r.save(str(tmp_path / 'ckpt'))
     back = State.from_file(str(tmp_path / 'ckpt'))
     assert np.array_equal(back.to_numpy(), r.to_numpy()) and back.subspace == r.subspace
+    # byte-level: PETSc's binary Vec = VEC_FILE_CLASSID (1211214) and the length as big-endian PetscInt,
+    # then big-endian complex128.  A default PETSc build (32-bit PetscInt) is what save() writes; a
+    # --with-64-bit-indices file must load too, as must metadata that names the reference's module.
+    import pickle
+    import struct
+    raw = open(str(tmp_path / 'ckpt.vec'), 'rb').read()
+    assert raw[:8] == struct.pack('>ii', 1211214, 256) and len(raw) == 8 + 16 * 256
+    assert np.array_equal(np.frombuffer(raw[8:], dtype='>c16'), r.to_numpy())
+    r.save(str(tmp_path / 'ckpt64'), indices=64)
+    raw64 = open(str(tmp_path / 'ckpt64.vec'), 'rb').read()
+    assert raw64[:16] == struct.pack('>qq', 1211214, 256) and raw64[16:] == raw[8:]
+    assert np.array_equal(State.from_file(str(tmp_path / 'ckpt64')).to_numpy(), r.to_numpy())
+    meta = pickle.dumps(r.subspace, protocol=0).replace(b'dynamite_b200.subspaces', b'dynamite.subspaces')
+    assert b'dynamite.subspaces' in meta
+    open(str(tmp_path / 'ckpt64.metadata'), 'wb').write(meta)
+    assert State.from_file(str(tmp_path / 'ckpt64')).subspace == r.subspace
+    open(str(tmp_path / 'bad.vec'), 'wb').write(struct.pack('>ii', 7, 256) + raw[8:])
+    open(str(tmp_path / 'bad.metadata'), 'wb').write(pickle.dumps(r.subspace))
+    with pytest.raises(RuntimeError):
+        State.from_file(str(tmp_path / 'bad'))
     # projection
     p = r.copy()
     p.project(3, 1)
