@@ -156,6 +156,8 @@ struct dnm_mat_s {
   int tile_rows = 0;    // rows per thread in the tiled kernel: 0 auto, 8 or 16
   int pipeline = 0;     // pipelined persistent tiled kernel: 0 auto, 1 on, 2 off
   int jit = -1;         // operator-specialised (NVRTC) kernels for lean tiled passes: -1 auto, 0 off, 1 on
+  int autotune = -1;    // time a few plan shapes at the first MatMult of a big matrix: -1 auto, 0 off, 1 on
+  int tuned_shape = -1; // the shape the autotuner kept (index into TUNE_SHAPES), -1: none
   int far_bits = -1;    // outer positions a tiled pass may serve through the L2 (FAR masks): -1 auto
   int verbose = 0;
   dnm::TiledPlan *tiled = nullptr;

@@ -172,11 +172,42 @@ struct Group {
   int peer;
 };
 
+// the real group g and the imaginary group g+1 of one mask, each with a single sign mask (X and Y
+// fields on one site): one operand fetch serves both
+bool merge_at(const SmallTables &S, int g, int ngroups)
+{
+  if (g + 1 >= ngroups) return false;
+  const bool far0 = ((S.gd[g].w >> 17) & 1u) != 0, far1 = ((S.gd[g + 1].w >> 17) & 1u) != 0;
+  return S.lam[g] == S.lam[g + 1] && far0 == far1 && S.far[g] == S.far[g + 1] && S.peer[g] == S.peer[g + 1] &&
+         !(S.kp[g] & 1) && (S.kp[g + 1] & 1) && S.cf[2 * g + 1] == 0.0 && S.cf[2 * g + 3] == 0.0 && S.cf[2 * g] != 0.0 &&
+         S.cf[2 * g + 2] != 0.0;
+}
+
+// operand buffers a classic kernel needs for its folded remote masks
+int remote_groups(const PassDesc &pd)
+{
+  int n = 0;
+  const SmallTables &S = *pd.st;
+  for (int g = 0; g < pd.p->ngroups; ++g) {
+    const bool far = ((S.gd[g].w >> 17) & 1u) != 0;
+    const double A = S.cf[2 * g] + S.cf[2 * g + 1], Bc = S.cf[2 * g] - S.cf[2 * g + 1];
+    const bool merged = merge_at(S, g, pd.p->ngroups);
+    if (far && S.peer[g] != 0 && (merged || !(A == 0.0 && Bc == 0.0))) ++n;
+    if (merged) ++g;
+  }
+  return n;
+}
+
 // acc[r] += D_g(row) * x[row ^ mask_g] for every group of the pass.  `tile` = the staged tile,
 // `x` = the global operand (far groups), `tid`, `og` (tile-uniform index bits) and `base` (this
 // thread's index without the row offsets) are in scope.
-void gen_groups(Out &o, const PassDesc &pd, const Geo &g_)
+// remote_mode 0: groups that read another rank's shard load it straight into registers;
+// 1: emit ONLY the asynchronous copies (cp.async, peer memory -> shared buffer k of the pass) of the
+//    remote groups, under the same activity conditions as the arithmetic; 2: every group, the remote
+//    ones reading their shared buffer (NVLink latency is then paid once per tile, behind the local work)
+void gen_groups(Out &o, const PassDesc &pd, const Geo &g_, int remote_mode = 0)
 {
+  int remote_index = -1;
   const PassParams &P = *pd.p;
   const SmallTables &S = *pd.st;
   const int R = g_.R, LOG_NT = g_.LOG_NT, NT = g_.NT;
@@ -201,11 +232,82 @@ void gen_groups(Out &o, const PassDesc &pd, const Geo &g_)
     const int HI = (int)(G.lam >> LOG_NT);
     const u32 s1t = G.s1w & (u32)(NT - 1), sBt = G.sBw & (u32)(NT - 1);
     const u32 s1r = G.s1w >> LOG_NT, sBr = G.sBw >> LOG_NT;
+    if (merge_at(S, g, P.ngroups)) {
+      // X and Y field on one site: D = +-cr + i (+-ci), one fetch
+      const bool remote_m = G.far && G.peer != 0;
+      if (remote_m) ++remote_index;
+      const int gi = g + 1;
+      ++g;
+      if (remote_mode == 1 && !remote_m) continue;
+      const bool issue_m = remote_mode == 1, staged_m = remote_mode == 2 && remote_m;
+      if (staged_m && remote_index == 0) o("    cpa_wait_all();  // the staged remote operands (each thread reads back only what it copied)\n");
+      const double cr = S.cf[2 * (gi - 1)], ci = S.cf[2 * gi];
+      const u32 sit = S.sw[2 * gi] & (u32)(NT - 1), sir = S.sw[2 * gi] >> LOG_NT;
+      if (remote_m && pd.filter_bit >= 0)
+        o("    if (((og >> %d) & 1) == %d)  // this pass serves the folded remote masks on half of the tiles\n", pd.filter_bit, pd.filter_val);
+      o("    {  // groups %d+%d: mask window 0x%x%s, real %s + imaginary %s, one fetch\n", gi - 1, gi, G.lam, G.far ? " FAR" : "",
+        hexd(cr).c_str(), hexd(ci).c_str());
+      auto expo_m = [&](i64 so, u32 st) -> std::string {
+        std::string e;
+        char buf[128];
+        if (so != 0) {
+          snprintf(buf, sizeof(buf), "(__popcll((u64)(og & 0x%llxll)) & 1)", (u64)so);
+          e = buf;
+        }
+        if (st != 0) {
+          snprintf(buf, sizeof(buf), "(__popc(tid & 0x%xu) & 1)", st);
+          if (!e.empty()) e += " ^ ";
+          e += buf;
+        }
+        return e;
+      };
+      const std::string er = expo_m(G.so1, s1t), ei = expo_m(S.so[2 * gi], sit);
+      if (!issue_m) {
+        if (er.empty()) o("      const double cr = %s;\n", hexd(cr).c_str());
+        else o("      const double cr = (%s) ? %s : %s;\n", er.c_str(), hexd(-cr).c_str(), hexd(cr).c_str());
+        if (ei.empty()) o("      const double ci = %s;\n", hexd(ci).c_str());
+        else o("      const double ci = (%s) ? %s : %s;\n", ei.c_str(), hexd(-ci).c_str(), hexd(ci).c_str());
+      }
+      if (staged_m) o("      const double2 *src = tile + %d + tid;  // staged copy of the operand from rank ^ %d\n", (1 + remote_index) << g_.T, G.peer);
+      else if (G.far && G.peer) o("      const double2 *src = xs.p[%d] + (base ^ 0x%llxll);  // rank ^ %d over NVLink\n", G.peer, (u64)((i64)G.farmask & ~g_.rowbits), G.peer);
+      else if (G.far) o("      const double2 *src = x + (base ^ 0x%llxll);\n", (u64)((i64)G.farmask & ~g_.rowbits));
+      else o("      const double2 *src = tile + (tid ^ 0x%xu);\n", lamlo);
+      for (int h = 0; h < R; h += 4) {
+        o("      {\n");
+        for (int r = h; r < std::min(R, h + 4); ++r) {
+          if (issue_m) {
+            o("        cpa16(&tile[%d + tid + %d], src + 0x%llxll);\n", (1 + remote_index) << g_.T, r * NT, (u64)g_.roff[r ^ HI]);
+            continue;
+          }
+          char opnd[128];
+          if (staged_m) snprintf(opnd, sizeof(opnd), "src[%d]", r * NT);
+          else if (G.far) snprintf(opnd, sizeof(opnd), "__ldcg(src + 0x%llxll)", (u64)g_.roff[r ^ HI]);
+          else snprintf(opnd, sizeof(opnd), "src[%d]", (r ^ HI) * NT);
+          o("        const double2 v%d = %s;\n", r, opnd);
+        }
+        if (!issue_m)
+          for (int r = h; r < std::min(R, h + 4); ++r) {
+            const bool nr = par32(s1r & (u32)r) != 0, ni = par32(sir & (u32)r) != 0;
+            o("        ar%d = fma(%scr, v%d.x, ar%d); ai%d = fma(%scr, v%d.y, ai%d); ar%d = fma(%sci, v%d.y, ar%d); ai%d = fma(%sci, v%d.x, ai%d);\n",
+              r, nr ? "-" : "", r, r, r, nr ? "-" : "", r, r, r, ni ? "" : "-", r, r, r, ni ? "-" : "", r, r);
+          }
+        o("      }\n");
+      }
+      o("    }\n");
+      continue;
+    }
     // D(row) = (-1)^(e1 ^ k1(r)) * ((eB ^ kB(r)) ? c1 - c2 : c1 + c2): e = tile and thread part of the
     // sign exponents (run time), k = row part (known here)
     const double A = G.c1 + G.c2, Bc = G.c1 - G.c2;
     if (A == 0.0 && Bc == 0.0) continue;
+    const bool remote = G.far && G.peer != 0;
+    if (remote) ++remote_index;
+    if (remote_mode == 1 && !remote) continue;
+    const bool issue = remote_mode == 1, staged = remote_mode == 2 && remote;
+    if (staged && remote_index == 0) o("    cpa_wait_all();  // the staged remote operands (each thread reads back only what it copied)\n");
 
+    if (remote && pd.filter_bit >= 0)
+      o("    if (((og >> %d) & 1) == %d)  // this pass serves the folded remote masks on half of the tiles\n", pd.filter_bit, pd.filter_val);
     o("    {  // group %d: mask window 0x%x%s%s, c1=%s c2=%s\n", g, G.lam, G.imag ? " imag" : "", G.far ? " FAR" : "",
       hexd(G.c1).c_str(), hexd(G.c2).c_str());
     auto expo = [&](i64 so, u32 st) -> std::string {
@@ -225,16 +327,23 @@ void gen_groups(Out &o, const PassDesc &pd, const Geo &g_)
     const std::string e1 = expo(G.so1, s1t), eB = expo(G.soB, sBt);
     if (!e1.empty()) o("      const int e1 = %s;\n", e1.c_str());
     if (!eB.empty()) o("      const int eB = %s;\n", eB.c_str());
-    if (G.far && G.peer) o("      const double2 *src = xs.p[%d] + (base ^ 0x%llxll);  // rank ^ %d over NVLink\n", G.peer, (u64)((i64)G.farmask & ~g_.rowbits), G.peer);
+    if (staged) o("      const double2 *src = tile + %d + tid;  // staged copy of the operand from rank ^ %d\n", (1 + remote_index) << g_.T, G.peer);
+    else if (G.far && G.peer) o("      const double2 *src = xs.p[%d] + (base ^ 0x%llxll);  // rank ^ %d over NVLink\n", G.peer, (u64)((i64)G.farmask & ~g_.rowbits), G.peer);
     else if (G.far) o("      const double2 *src = x + (base ^ 0x%llxll);\n", (u64)((i64)G.farmask & ~g_.rowbits));
     else o("      const double2 *src = tile + (tid ^ 0x%xu);\n", lamlo);
     auto operand = [&](int r) -> std::string {
       char buf[128];
-      if (G.far) snprintf(buf, sizeof(buf), "__ldcg(src + 0x%llxll)", (u64)g_.roff[r ^ HI]);
+      if (staged) snprintf(buf, sizeof(buf), "src[%d]", r * NT);
+      else if (G.far) snprintf(buf, sizeof(buf), "__ldcg(src + 0x%llxll)", (u64)g_.roff[r ^ HI]);
       else snprintf(buf, sizeof(buf), "src[%d]", (r ^ HI) * NT);
       return buf;
     };
     auto emit_rows = [&](const std::vector<int> &rows, const char *cv, const char *indent) {
+      if (issue) {
+        for (int r : rows)
+          o("%scpa16(&tile[%d + tid + %d], src + 0x%llxll);\n", indent, (1 + remote_index) << g_.T, r * NT, (u64)g_.roff[r ^ HI]);
+        return;
+      }
       for (size_t h = 0; h < rows.size(); h += 4) {
         const size_t e = std::min(rows.size(), h + 4);
         o("%s{\n", indent);
@@ -328,16 +437,25 @@ void gen_classic(Out &o, const PassDesc &pd, int index)
   o("    const i64 og = outer | rank_bits;  // index bits shared by the tile (signs)\n");
   o("    const i64 base = outer | %s;\n", deposit_expr("tid", pd.W, 0, g.LOG_NT).c_str());
   for (int r = 0; r < R; ++r) o("    cpa16(&tile[tid + %d], x + (base | 0x%llxll));\n", r * NT, (u64)g.roff[r]);
+  const int nrem = remote_groups(pd);
+  if (nrem) {
+    // operands of the folded remote masks: asynchronous copies from the partners' shards over NVLink into
+    // their own buffers, in flight while the local masks are evaluated
+    o("    cpa_commit();\n");
+    gen_groups(o, pd, g, 1);
+    o("    cpa_commit();\n");
+  }
   // the cached diagonal is in flight together with the tile
   for (int r = 0; r < R; ++r) o("    double dg%d = 0.0;\n", r);
   o("    if (diag != nullptr) {\n");
   for (int r = 0; r < R; ++r) o("      dg%d = %s(diag + (base | 0x%llxll));\n", r, hint_ld(), (u64)g.roff[r]);
   o("    }\n");
-  o("    cpa_wait();\n    __syncthreads();\n");
+  if (nrem) o("    cpa_wait_first();\n    __syncthreads();\n");
+  else o("    cpa_wait();\n    __syncthreads();\n");
   o("%s", acc_decl(R).c_str());
   for (int r = 0; r < R; ++r)
     o("    { const double2 v = tile[tid + %d]; ar%d = dg%d * v.x; ai%d = dg%d * v.y; }\n", r * NT, r, r, r, r);
-  gen_groups(o, pd, g);
+  gen_groups(o, pd, g, nrem ? 2 : 0);
   if (P.accumulate == 1) {
     o("    __syncthreads();\n");
     for (int r = 0; r < R; ++r) o("    cpa16(&tile[tid + %d], y + (base | 0x%llxll));\n", r * NT, (u64)g.roff[r]);
@@ -570,6 +688,9 @@ const char *PRELUDE =
     "__device__ __forceinline__ void cpa16(void *s, const void *g)\n{\n"
     "  asm volatile(\"cp.async.cg.shared.global [%0], [%1], 16;\\n\" ::\"r\"(smem_u32(s)), \"l\"(g) : \"memory\");\n}\n"
     "__device__ __forceinline__ void cpa_wait() { asm volatile(\"cp.async.commit_group;\\ncp.async.wait_group 0;\\n\" ::: \"memory\"); }\n"
+    "__device__ __forceinline__ void cpa_commit() { asm volatile(\"cp.async.commit_group;\\n\" ::: \"memory\"); }\n"
+    "__device__ __forceinline__ void cpa_wait_all() { asm volatile(\"cp.async.wait_group 0;\\n\" ::: \"memory\"); }\n"
+    "__device__ __forceinline__ void cpa_wait_first() { asm volatile(\"cp.async.wait_group 1;\\n\" ::: \"memory\"); }\n"
     "__device__ __forceinline__ void st_plain(double2 *p, double2 v) { *p = v; }\n"
     "__device__ __forceinline__ void mbar_init(u64 *bar, int count)\n{\n"
     "  asm volatile(\"mbarrier.init.shared::cta.b64 [%0], %1;\" ::\"r\"(smem_u32(bar)), \"r\"(count));\n}\n"
@@ -677,7 +798,7 @@ Module *compile(const std::string &src, const std::vector<PassDesc> &passes, std
         kn.box[i] = bx.box[i];
       }
     } else {
-      kn.smem = (size_t)16 << pd.T;
+      kn.smem = ((size_t)16 << pd.T) * (size_t)(1 + remote_groups(pd));
     }
     d.funcSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)kn.smem);
     d.funcSetAttribute(f, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100);
@@ -747,7 +868,9 @@ void launch(const Kernel &k, unsigned long long ntiles, int sm_count, cudaStream
     rc = driver().launchKernel((CUfunction)k.func, (unsigned)ntiles, 1, 1, (unsigned)k.threads, 1, 1, (unsigned)k.smem,
                                (CUstream)stream, args, nullptr);
   }
-  DNM_REQUIRE(rc == CUDA_SUCCESS, DNM_ERR_CUDA, "cuLaunchKernel of a generated MatMult pass failed (%d)", (int)rc);
+  DNM_REQUIRE(rc == CUDA_SUCCESS, DNM_ERR_CUDA,
+              "cuLaunchKernel of a generated MatMult pass failed (%d): tiles=%llu threads=%d smem=%zu pipelined=%d", (int)rc,
+              ntiles, k.threads, k.smem, (int)k.pipelined);
 }
 
 }  // namespace jit

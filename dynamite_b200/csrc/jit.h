@@ -55,6 +55,8 @@ struct PassDesc {
   int T = 0;
   int nloc = 0;        // index bits on this rank
   std::vector<int> W;  // window positions, W[j] = index bit of window coordinate j (ascending)
+  // folded remote masks only on the tiles whose index bit filter_bit equals filter_val (-1: all tiles)
+  int filter_bit = -1, filter_val = 0;
   // shape of the generated kernel
   bool pipelined = false;
   int rows = 8;  // rows per thread (4 or 8)

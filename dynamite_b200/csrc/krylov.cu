@@ -303,7 +303,7 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
     m = (int)fit - 1;
   }
   DNM_REQUIRE(m >= 1, DNM_ERR_ARG, "Krylov dimension must be at least 1");
-  if (max_it <= 0) max_it = (int)std::max<int64_t>(100, 2 * N / m);  // SLEPc default
+  if (max_it <= 0) max_it = (int)std::min<int64_t>(2147483647, std::max<int64_t>(100, 2 * N / m));  // SLEPc default
 
   const double t_out = std::abs(tscale);
   if (t_out == 0.0) {
@@ -555,7 +555,7 @@ extern "C" int dnm_eigsolve(dnm_mat_t A, int nev, int which, double tol, int max
     ncv = (int)fit - 1;
   }
   DNM_REQUIRE(ncv >= nev && ncv <= 512, DNM_ERR_ARG, "bad ncv=%d for nev=%d", ncv, nev);
-  if (max_it <= 0) max_it = (int)std::max<int64_t>(100, 2 * N / ncv);
+  if (max_it <= 0) max_it = (int)std::min<int64_t>(2147483647, std::max<int64_t>(100, 2 * N / ncv));
 
   Basis B;
   B.nloc = nloc;

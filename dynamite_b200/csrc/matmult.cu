@@ -567,6 +567,10 @@ extern "C" int dnm_mat_set_option(dnm_mat_t A, const char *key, int64_t value)
     DNM_REQUIRE(value >= -1 && value <= 1, DNM_ERR_ARG, "jit must be -1 (auto), 0 (off) or 1 (on)");
     A->jit = (int)value;
     tiled_free(A);
+  } else if (!strcmp(key, "autotune")) {
+    DNM_REQUIRE(value >= -1 && value <= 1, DNM_ERR_ARG, "autotune must be -1 (auto), 0 (off) or 1 (on)");
+    A->autotune = (int)value;
+    tiled_free(A);
   } else if (!strcmp(key, "far_bits")) {
     DNM_REQUIRE(value >= -1 && value <= 16, DNM_ERR_ARG, "far_bits must be -1 (auto) or in [0,16]");
     A->far_bits = (int)value;
@@ -595,6 +599,7 @@ extern "C" int dnm_mat_get_info(dnm_mat_t A, const char *key, double *value)
   else if (!strcmp(key, "launches_per_mult")) *value = A->launches_per_mult;
   else if (!strcmp(key, "has_diag")) *value = A->d_diag ? 1.0 : 0.0;
   else if (!strcmp(key, "jit_passes")) *value = tiled_jit_passes(A);
+  else if (!strcmp(key, "tuned_shape")) *value = A->tuned_shape;
   else DNM_REQUIRE(false, DNM_ERR_ARG, "unknown info key '%s'", key);
   DNM_API_END
 }

@@ -180,6 +180,14 @@ struct Pass {
   int nmasks = 0;
   int nfar = 0;      // masks served through the L2 window (FAR groups)
   int nremote = 0;   // ... of which read another rank's shard (folded remote masks: generated kernels only)
+  // what the pass was built from (so that the planner can rebuild it with the folded remote masks)
+  std::vector<const NMask *> src_local, src_fold;
+  size_t src_nfar = 0;
+  i64 Fbits = 0;
+  int Bbits = 0;
+  // folded remote masks are evaluated only on the tiles whose index bit `filter_bit` equals `filter_val`
+  // (the other half of the rows is served by another pass: the NVLink volume is spread over two passes)
+  int filter_bit = -1, filter_val = 0;
   i64 wbits = 0;     // window bit positions
   std::vector<int> W;               // the same as a list: W[j] = index bit of window coordinate j
   const jit::Kernel *jk = nullptr;  // operator-specialised kernel of this pass (owned by TiledPlan::jit)
@@ -860,22 +868,54 @@ void plan_group(TiledPlan &plan, std::vector<const NMask *> remaining, int peer_
       ps = make_pass(chosen, Wpos, T, R, B, nloc, wrote ? 1 : 0);
     }
     for (size_t k = 0; k < remaining.size(); ++k) taken[k] = taken[k] || taken_far[k];
-    if (fold && !fold->empty() && chosen_ok && ps.small && ps.p.lean &&
-        (size_t)ps.p.ngroups + 2 * fold->size() <= (size_t)SMALL_GROUPS &&
-        (size_t)ps.nterms + 4 * fold->size() <= (size_t)SMALL_TERMS) {
-      std::vector<const NMask *> all3(chosen);
-      all3.insert(all3.end(), farm.begin(), farm.end());
-      all3.insert(all3.end(), fold->begin(), fold->end());
-      Pass folded = make_pass(all3, Wpos, T, R, B, nloc, wrote ? 1 : 0, farm.size() + fold->size(), F);
-      if (folded.small && folded.p.lean) {
-        for (void *q : ps.owned) cudaFree(q);
-        ps = std::move(folded);
-        fold->clear();
-      } else {
-        for (void *q : folded.owned) cudaFree(q);
+    if (fold && !fold->empty() && chosen_ok && ps.small && ps.p.lean) {
+      // spread the NVLink volume over the passes: half of the remote masks here when another pass follows
+      bool more_passes = false;
+      for (size_t k = 0; k < remaining.size(); ++k) more_passes = more_passes || !taken[k];
+      (void)more_passes;
+      size_t take = fold->size();
+      // every folded group stages its operand in a shared-memory buffer of its own next to the tile (one per
+      // mask, two when its real and imaginary parts cannot share the fetch)
+      {
+        auto buffers = [](const NMask *nm) {
+          int nre = 0, nim = 0;
+          std::vector<i64> sre, sim;
+          for (const NTerm &t : nm->terms) {
+            std::vector<i64> &v = t.imag ? sim : sre;
+            if (std::find(v.begin(), v.end(), t.sign) == v.end()) v.push_back(t.sign);
+            (t.imag ? nim : nre) += 1;
+          }
+          if (nre && nim && !(sre.size() == 1 && sim.size() == 1)) return 2;
+          return 1;
+        };
+        const size_t room = (size_t)(200 * 1024) / ((size_t)16 << T) - 1;
+        size_t used = 0, fit = 0;
+        while (fit < take && used + buffers((*fold)[fit]) <= room) used += buffers((*fold)[fit++]);
+        take = fit;
+      }
+      while (take > 0 && ((size_t)ps.p.ngroups + 2 * take > (size_t)SMALL_GROUPS || (size_t)ps.nterms + 4 * take > (size_t)SMALL_TERMS))
+        --take;
+      if (take > 0) {
+        std::vector<const NMask *> all3(chosen);
+        all3.insert(all3.end(), farm.begin(), farm.end());
+        all3.insert(all3.end(), fold->begin(), fold->begin() + take);
+        Pass folded = make_pass(all3, Wpos, T, R, B, nloc, wrote ? 1 : 0, farm.size() + take, F);
+        if (folded.small && folded.p.lean) {
+          for (void *q : ps.owned) cudaFree(q);
+          ps = std::move(folded);
+          ps.src_fold.assign(fold->begin(), fold->begin() + take);
+          fold->erase(fold->begin(), fold->begin() + take);
+        } else {
+          for (void *q : folded.owned) cudaFree(q);
+        }
       }
     }
     ps.peer_xor = peer_xor;
+    ps.src_local = chosen;
+    ps.src_local.insert(ps.src_local.end(), farm.begin(), farm.end());
+    ps.src_nfar = farm.size();
+    ps.Fbits = F;
+    ps.Bbits = B;
     if (verbose)
       fprintf(stderr, "[dnm] pass %zu: peer^%d window=0x%llx far=0x%llx masks=%d (%d far) terms=%d %s\n",
               plan.passes.size(), peer_xor, (unsigned long long)W, (unsigned long long)F, ps.nmasks, ps.nfar, ps.nterms,
@@ -1162,6 +1202,57 @@ std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &mas
       }
     }
     if (plan->fold && !fold.empty()) plan->fold_failed = true;  // no lean pass could take the remote masks
+    // Spread the NVLink volume: a second lean pass evaluates the same folded masks on the other half of
+    // the rows (split by an index bit that lies outside both windows, i.e. per tile).
+    if (plan->fold && !plan->fold_failed && getenv("DNM_NO_FOLD_SPLIT") == nullptr) {
+      int ia = -1, ib = -1;
+      for (size_t k = 0; k < plan->passes.size(); ++k)
+        if (!plan->passes[k].src_fold.empty()) ia = (int)k;
+      size_t holders = 0;
+      for (const Pass &ps : plan->passes) holders += ps.src_fold.empty() ? 0 : 1;
+      if (ia >= 0 && holders == 1) {
+        const Pass &pa = plan->passes[ia];
+        for (size_t k = 0; k < plan->passes.size() && ib < 0; ++k) {
+          const Pass &pb = plan->passes[k];
+          if ((int)k == ia || !(pb.small && pb.p.lean && pb.peer_xor == 0 && pb.R <= 8)) continue;
+          if ((size_t)pb.p.ngroups + 2 * pa.src_fold.size() > (size_t)SMALL_GROUPS ||
+              (size_t)pb.nterms + 4 * pa.src_fold.size() > (size_t)SMALL_TERMS)
+            continue;
+          ib = (int)k;
+        }
+        if (ib >= 0) {
+          const i64 lmask = ((i64)1 << nloc) - 1;
+          const i64 common = ~(plan->passes[ia].wbits | plan->passes[ib].wbits) & lmask;
+          int q = -1;
+          for (int b = nloc - 1; b >= 0 && q < 0; --b)
+            if ((common >> b) & 1) q = b;
+          if (q >= 0) {
+            Pass &pb = plan->passes[ib];
+            std::vector<const NMask *> all3(pb.src_local);
+            all3.insert(all3.end(), pa.src_fold.begin(), pa.src_fold.end());
+            Pass nb = make_pass(all3, pb.W, pb.T, pb.R, pb.Bbits, nloc, pb.p.accumulate, pb.src_nfar + pa.src_fold.size(), pb.Fbits);
+            if (nb.small && nb.p.lean) {
+              nb.peer_xor = 0;
+              nb.src_local = pb.src_local;
+              nb.src_fold = pa.src_fold;
+              nb.src_nfar = pb.src_nfar;
+              nb.Fbits = pb.Fbits;
+              nb.Bbits = pb.Bbits;
+              nb.filter_bit = q;
+              nb.filter_val = 1;
+              for (void *p : pb.owned) cudaFree(p);
+              pb = std::move(nb);
+              plan->passes[ia].filter_bit = q;
+              plan->passes[ia].filter_val = 0;
+              if (verbose)
+                fprintf(stderr, "[dnm] folded remote masks split over passes %d and %d by index bit %d\n", ia, ib, q);
+            } else {
+              for (void *p : nb.owned) cudaFree(p);
+            }
+          }
+        }
+      }
+    }
   }
   // cost in vector sweeps over HBM: a writing pass reads x and writes y (2), an
   // accumulating pass also re-reads y (3); a direct gather re-reads x once per mask.
@@ -1182,7 +1273,15 @@ std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &mas
   return plan;
 }
 
-TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false)
+// shapes tried by the first-use autotuner (tile bits, run bits, L2-window positions); -1 in T = the
+// generic-kernel default plan
+struct TuneShape {
+  int T, B, f;
+};
+const TuneShape TUNE_SHAPES[] = {{11, 4, 10}, {12, 4, 7}, {13, 4, 0}, {12, 4, 0}, {-1, 0, 0}};
+constexpr int N_TUNE_SHAPES = 5;
+
+TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false, int tune = -1)
 {
   const int n = ilog2(A->M);
   const int nloc = n - ilog2(G.nranks);
@@ -1221,10 +1320,20 @@ TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false)
     const int B = env_b ? std::max(0, std::min(atoi(env_b), 7)) : 4;
     candidates.push_back(Cand{11, B, std::min(10, nloc - 11), true});
   }
+  if (tune >= 0 && TUNE_SHAPES[tune].T > 0) {
+    // autotuner: exactly this shape, generated kernels wherever its passes are lean
+    const TuneShape &ts = TUNE_SHAPES[tune];
+    candidates.clear();
+    const int T = std::min(ts.T, nloc);
+    candidates.push_back(Cand{T, std::min(ts.B, T - 4), std::min(ts.f, nloc - T), false});
+  } else if (tune >= 0) {
+    // the default plan of the generic kernel (no generated code): drop the jit-oriented candidate
+    if (candidates.size() > 1 && candidates.back().for_jit) candidates.pop_back();
+  }
   std::unique_ptr<TiledPlan> best;
   Cand best_c{0, 0, 0, false};
   for (const Cand &c : candidates) {
-    const bool fold_ok = jit_possible && G.nranks > 1 && !no_fold;
+    const bool fold_ok = jit_possible && G.nranks > 1 && !no_fold && !(tune >= 0 && TUNE_SHAPES[tune].T < 0);
     std::unique_ptr<TiledPlan> cand = plan_with(A, masks, c.T, rows_for(c.T, A->tile_rows), c.B, c.f, A->verbose, fold_ok);
     if (cand->fold_failed) cand = plan_with(A, masks, c.T, rows_for(c.T, A->tile_rows), c.B, c.f, A->verbose, false);
     if (A->verbose)
@@ -1286,7 +1395,8 @@ TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false)
   }
   // Operator-specialised kernels for the lean passes (jit.h): on by default for vectors that leave
   // the L2 (the generic kernel is kept for small problems, where compiling would dominate).
-  const bool want_jit = A->jit == 1 || (A->jit < 0 && getenv("DNM_NO_JIT") == nullptr && best && best->nloc >= 22);
+  const bool want_jit = !(tune >= 0 && TUNE_SHAPES[tune].T < 0) &&
+                        (A->jit == 1 || (A->jit < 0 && getenv("DNM_NO_JIT") == nullptr && best && best->nloc >= 22));
   if (best && want_jit && !best->d_batch) {
     std::vector<jit::PassDesc> descs;
     std::vector<size_t> which;
@@ -1299,6 +1409,8 @@ TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false)
       d.T = ps.T;
       d.nloc = best->nloc;
       d.W = ps.W;
+      d.filter_bit = ps.filter_bit;
+      d.filter_val = ps.filter_val;
       d.rows = 8;
       if (const char *e = getenv("DNM_JIT_ROWS")) d.rows = atoi(e) == 4 ? 4 : 8;
       d.nbuf = ps.p.accumulate == 1 ? 2 : 3;
@@ -1328,7 +1440,7 @@ TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false)
         // folded remote masks only exist in generated code: plan again the classic way
         if (A->verbose) fprintf(stderr, "[dnm] generated kernels unavailable (%s): planning without folded remote masks\n", log.c_str());
         best.reset();
-        return build_plan(A, true);
+        return build_plan(A, true, tune);
       }
       if (best->jit) {
         for (size_t k = 0; k < which.size(); ++k) best->passes[which[k]].jk = &best->jit->kernels[k];
@@ -1336,7 +1448,7 @@ TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false)
         for (const Pass &ps : best->passes) stranded = stranded || (ps.nremote > 0 && !ps.jk);
         if (stranded && !no_fold) {
           best.reset();
-          return build_plan(A, true);
+          return build_plan(A, true, tune);
         }
         if (A->verbose) fprintf(stderr, "[dnm] %zu generated kernels (%zu bytes of source)\n", which.size(), src.size());
       } else if (A->verbose || A->jit == 1) {
@@ -1380,10 +1492,90 @@ int tiled_jit_passes(dnm_mat_s *A)
 
 int tiled_passes(dnm_mat_s *A) { return A->tiled ? (int)(A->tiled->passes.size() + A->tiled->directs.size()) : 0; }
 
+namespace {
+void run_plan(dnm_mat_s *A, TiledPlan &plan, dnm_vec_t xv, dnm_vec_t yv);
+
+// First use of a big matrix: time a few plan shapes on the caller's own vectors and keep the
+// fastest (which shape wins depends on the operator: XX+YY models skip half of the rows of every
+// mask and like a wide L2 window, field-heavy models are bound by the operand fetches instead).
+// Sharded: every rank runs the same trials and the slowest rank's time decides, so all ranks agree.
+TiledPlan *autotune_plan(dnm_mat_s *A, dnm_vec_t xv, dnm_vec_t yv)
+{
+  const int nloc = ilog2(A->M) - ilog2(G.nranks);
+  const bool jit_possible = A->jit != 0 && getenv("DNM_NO_JIT") == nullptr && (A->jit == 1 || nloc >= 22);
+  const bool wanted = A->autotune == 1 || (A->autotune < 0 && getenv("DNM_NO_AUTOTUNE") == nullptr && nloc >= 24);
+  if (!wanted || !jit_possible || A->tile_bits || A->far_bits >= 0 || getenv("DNM_FAR_BITS") || getenv("DNM_REMOTE"))
+    return build_plan(A);
+  std::unique_ptr<TiledPlan> best;
+  float best_ms = 0.f;
+  int best_shape = -1;
+  cudaEvent_t e0, e1;
+  DNM_CHECK_CUDA(cudaEventCreate(&e0));
+  DNM_CHECK_CUDA(cudaEventCreate(&e1));
+  for (int k = 0; k < N_TUNE_SHAPES; ++k) {
+    if (TUNE_SHAPES[k].T < 0 && G.nranks > 1) continue;  // (its remote groups would allocate whole-shard staging buffers)
+    if (TUNE_SHAPES[k].T > nloc - 1) continue;
+    std::unique_ptr<TiledPlan> cand;
+    try {
+      cand.reset(build_plan(A, false, k));
+    } catch (const Fail &) {
+      continue;
+    }
+    if (!cand) continue;
+    bool dup = false;  // identical to the best so far in every pass window: nothing new to learn
+    if (best && best->passes.size() == cand->passes.size()) {
+      dup = true;
+      for (size_t i = 0; i < cand->passes.size(); ++i)
+        dup = dup && cand->passes[i].wbits == best->passes[i].wbits && cand->passes[i].nfar == best->passes[i].nfar &&
+              (cand->passes[i].jk != nullptr) == (best->passes[i].jk != nullptr);
+    }
+    if (dup) continue;
+    float ms = 0.f;
+    try {
+      run_plan(A, *cand, xv, yv);  // warm-up (module load, first touch)
+      DNM_CHECK_CUDA(cudaEventRecord(e0, G.stream));
+      run_plan(A, *cand, xv, yv);
+      run_plan(A, *cand, xv, yv);
+      DNM_CHECK_CUDA(cudaEventRecord(e1, G.stream));
+      DNM_CHECK_CUDA(cudaEventSynchronize(e1));
+      DNM_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    } catch (const Fail &) {
+      cudaGetLastError();
+      continue;
+    }
+    if (G.nranks > 1) {
+      double v = ms;
+      DNM_CHECK_CUDA(cudaMemcpyAsync(G.d_scratch, &v, sizeof(double), cudaMemcpyHostToDevice, G.stream));
+      allreduce_max_dev(G.d_scratch, 1);
+      fetch_doubles(G.d_scratch, &v, 1);
+      ms = (float)v;
+    }
+    if (A->verbose)
+      fprintf(stderr, "[dnm] autotune shape T=%d B=%d far<=%d: %zu passes, %.3f ms per MatMult\n", TUNE_SHAPES[k].T,
+              TUNE_SHAPES[k].B, TUNE_SHAPES[k].f, cand->passes.size(), ms / 2);
+    if (!best || ms < best_ms) {
+      best = std::move(cand);
+      best_ms = ms;
+      best_shape = k;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (!best) return build_plan(A);
+  A->tuned_shape = best_shape;
+  return best.release();
+}
+}  // namespace
+
 void tiled_mult(dnm_mat_s *A, dnm_vec_t xv, dnm_vec_t yv)
 {
-  if (!A->tiled) A->tiled = build_plan(A);
-  TiledPlan &plan = *A->tiled;
+  if (!A->tiled) A->tiled = autotune_plan(A, xv, yv);
+  run_plan(A, *A->tiled, xv, yv);
+}
+
+namespace {
+void run_plan(dnm_mat_s *A, TiledPlan &plan, dnm_vec_t xv, dnm_vec_t yv)
+{
   const i64 nloc_rows = (i64)1 << plan.nloc;
   cplx *y = yv->d;
   int launches = 0;
@@ -1552,6 +1744,7 @@ void tiled_mult(dnm_mat_s *A, dnm_vec_t xv, dnm_vec_t yv)
   if (plan.any_remote) stream_barrier();  // peers are done reading x before it can change
   A->launches_per_mult = launches;
 }
+}  // namespace
 
 void tiled_diag(dnm_mat_s *A, double *d_diag)
 {

@@ -25,6 +25,7 @@ for tb, far, *rest in [tuple(int(v) for v in a.split(',')) for a in sys.argv[3:]
     bpetsc.precompute_diagonal(mat)
     mat.set_option('tile_bits', tb)
     mat.set_option('far_bits', far)
+    mat.set_option('verbose', int(os.environ.get('VERBOSE', '0')))
     mat.set_option('jit', rest[0] if rest else 0)
     mat.set_option('pipeline', rest[1] if len(rest) > 1 else 0)
     t0 = time.perf_counter()

@@ -83,9 +83,15 @@ def main():
                       rel_err(y5.vec[a:b], want[a:b]) < 1e-12, f'err={rel_err(y5.vec[a:b], want[a:b]):.2e}')
                 if name != 'SYK' and (diag or name == 'XX'):
                     check(f'generated kernels ran [{name}]', mat.get_info('jit_passes') >= 1)
-            mat.set_option('jit', -1)
             mat.set_option('far_bits', -1)
             os.environ.pop('DNM_REMOTE', None)
+            # the first-use autotuner: every rank runs the same trials, the slowest rank decides
+            mat.set_option('tile_bits', 0)
+            mat.set_option('autotune', 1)
+            y6 = H.dot(x)
+            check(f'matmult[autotuned] {name} L={L} diag={diag}', rel_err(y6.vec[a:b], want[a:b]) < 1e-12)
+            mat.set_option('autotune', -1)
+            mat.set_option('jit', -1)
             mat.set_option('tile_bits', 0)
             # DMA staging copies only the part of a partner shard this rank can touch (XX+YY terms:
             # half of it or nothing); the rest of the staging buffer is poisoned with NaNs here

@@ -154,6 +154,29 @@ def test_generated_kernels_vs_oracle(gpu, name, L, sub):
         mat.destroy()
 
 
+@pytest.mark.parametrize('name', ['MBL', 'long_range'])
+def test_autotuned_plan(gpu, name):
+    """First-use autotuner (forced on at a small size): times its plan shapes on the caller's vectors,
+    keeps one, and the product is still the oracle's."""
+    from dynamite_b200.hamiltonians import build_hamiltonian
+    L = 20
+    H = build_hamiltonian(name, L)
+    H.reduce_msc()
+    terms = [(int(m), int(s), complex(c)) for m, s, c in zip(H.msc['masks'], H.msc['signs'], H.msc['coeffs'])]
+    spec = {'type': 'full', 'L': L}
+    osub = oracle.Subspace(spec)
+    x = rand_state(osub.dim, 3)
+    want, _ = oracle.matmult_fast(oracle.Msc.from_terms(terms), osub, x, nthreads=8)
+    mat = product_mat(terms, spec, spec, False, precompute_diag=True)
+    mat.set_option('kernel', 2)
+    mat.set_option('jit', 1)
+    mat.set_option('autotune', 1)
+    assert rel_err(device_mult(mat, x), want) < TOL
+    assert mat.get_info('tuned_shape') >= 0
+    assert rel_err(device_mult(mat, x), want) < TOL      # the kept plan, second use
+    mat.destroy()
+
+
 def test_tiled_xparity(gpu):
     for tag in ('heisenberg_L7_xparity_plus', 'heisenberg_L7_xparity_minus', 'ising_L6_xparity_plus'):
         c = CASES[tag]
