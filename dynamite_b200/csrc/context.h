@@ -151,6 +151,7 @@ struct dnm_mat_s {
   std::vector<void *> owned;  // device allocations to free
   double *d_diag = nullptr;   // local_M doubles when precomputed
   double nrm = -1;
+  bool same_explicit = false;  // Explicit -> the same Explicit space (state lists compare equal)
   int kernel_pref = 0;  // 0 auto, 1 general, 2 tiled
   int tile_bits = 0;    // 0 auto
   int tile_rows = 0;    // rows per thread in the tiled kernel: 0 auto, 8 or 16

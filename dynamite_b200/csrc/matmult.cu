@@ -74,6 +74,107 @@ __global__ void __launch_bounds__(TPB)
   }
 }
 
+// Explicit / Auto -> the same sorted Explicit space.  The reference looks every column up with a
+// binary search over the whole sorted state list (bsubspace_impl.h:306-331; its own TODO at
+// bcuda_impl.cu:154-179 asks for shared memory): log2(dim) dependent global loads per (row, mask).
+// Here a CTA owns a block of EX_ROWS consecutive rows, whose kets (ascending) share every bit above
+// the highest bit in which the first and the last differ.  For a mask m all their images ket ^ m
+// therefore lie in ONE interval [P, P + 2^h) of state values: two threads bracket that interval in
+// the sorted list once per (block, mask) -- all masks in parallel -- the CTA stages that slice of the
+// list in shared memory with coalesced loads, and every row finishes its search there (typically
+// 8-11 shared-memory steps instead of 24 global ones at dim 10^7).  Bit-exact with S2I.
+constexpr int EX_ROWS = 256;
+constexpr int EX_CAP = 4096;       // staged slice, states
+constexpr int EX_MAX_MASKS = 256;  // bracket table, masks
+
+__device__ __forceinline__ i64 lower_bound_dev(const i64 *__restrict__ a, i64 lo, i64 len, i64 v)
+{
+  while (len > 0) {
+    const i64 half = len >> 1;
+    if (__ldg(&a[lo + half]) < v) {
+      lo += half + 1;
+      len -= half + 1;
+    } else {
+      len = half;
+    }
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(EX_ROWS)
+    k_mult_explicit(SubExplicit sub, MscDev msc, const double *__restrict__ diag, const cplx *__restrict__ x,
+                    cplx *__restrict__ y, i64 M)
+{
+  __shared__ i64 s_slice[EX_CAP];
+  __shared__ i64 s_lo[EX_MAX_MASKS], s_hi[EX_MAX_MASKS];
+  const int tid = threadIdx.x;
+  for (i64 row0 = (i64)blockIdx.x * EX_ROWS; row0 < M; row0 += (i64)gridDim.x * EX_ROWS) {
+    const i64 row = row0 + tid;
+    const bool ok = row < M;
+    const i64 last = min(row0 + (i64)EX_ROWS, M) - 1;
+    const i64 ket = ok ? __ldg(&sub.state_map[row]) : 0;
+    const i64 s_min = __ldg(&sub.state_map[row0]), s_max = __ldg(&sub.state_map[last]);
+    const i64 diff = s_min ^ s_max;
+    const int h = diff ? 64 - __clzll(diff) : 0;  // bits [0, h) vary inside the block
+    const i64 lowmask = (h >= 63) ? (i64)0x7fffffffffffffffll : (((i64)1 << h) - 1);
+    // bracket the image interval of every mask (2 searches per mask, all in parallel)
+    __syncthreads();  // the previous block's tables are no longer in use
+    for (int k = tid; k < 2 * msc.nmasks; k += EX_ROWS) {
+      const int mi = k >> 1;
+      const i64 P = (s_min ^ __ldg(&msc.masks[mi])) & ~lowmask;
+      if (k & 1) {
+        // first state >= P + 2^h (the whole list when the interval reaches the top)
+        s_hi[mi] = (h >= 63) ? sub.n : lower_bound_dev(sub.rmap_states, 0, sub.n, P + lowmask + 1);
+      } else {
+        s_lo[mi] = lower_bound_dev(sub.rmap_states, 0, sub.n, P);
+      }
+    }
+    double ar = 0.0, ai = 0.0;
+    int mi = 0;
+    if (diag != nullptr) {
+      if (ok) {
+        const cplx xv = x[row];
+        const double d = diag[row];
+        ar = d * xv.x;
+        ai = d * xv.y;
+      }
+      mi = 1;
+    }
+    __syncthreads();
+    for (; mi < msc.nmasks; ++mi) {
+      const i64 c_lo = s_lo[mi], len = s_hi[mi] - c_lo;
+      const i64 bra = ket ^ __ldg(&msc.masks[mi]);
+      i64 col = -1;
+      if (len > 0 && len <= EX_CAP) {
+        __syncthreads();  // everybody is done with the previous slice
+        for (i64 i = tid; i < len; i += EX_ROWS) s_slice[i] = __ldg(&sub.rmap_states[c_lo + i]);
+        __syncthreads();
+        int lo = 0, n = (int)len;
+        while (n > 0) {
+          const int half = n >> 1;
+          if (s_slice[lo + half] < bra) {
+            lo += half + 1;
+            n -= half + 1;
+          } else {
+            n = half;
+          }
+        }
+        if (lo < (int)len && s_slice[lo] == bra) col = c_lo + lo;
+      } else if (len > 0) {
+        const i64 pos = lower_bound_dev(sub.rmap_states, c_lo, len, bra);
+        if (pos < c_lo + len && __ldg(&sub.rmap_states[pos]) == bra) col = pos;
+      }
+      if (!ok || col < 0) continue;  // outside the subspace
+      double cr, ci;
+      mask_element(msc, mi, bra, cr, ci);
+      const cplx xv = x[col];
+      ar += cr * xv.x - ci * xv.y;
+      ai += cr * xv.y + ci * xv.x;
+    }
+    if (ok) y[row] = make_double2(ar, ai);
+  }
+}
+
 // SpinConserve -> the same SpinConserve sector (the BASELINE eigsolve config): the row index IS
 // the rank of the ket, so the column is row + rank_delta over the few bits the mask spans, and
 // the binomial table is staged in shared memory.  Bit-exact with S2I (tests/test_gpu_matmult.py).
@@ -327,6 +428,15 @@ void general_mult(dnm_mat_s *A, const cplx *x, cplx *y)
       return;
     }
   }
+  if (l.type == DNM_EXPLICIT && r.type == DNM_EXPLICIT && A->same_explicit && A->left.rmap_idx.empty() &&
+      A->msc.nmasks <= EX_MAX_MASKS && getenv("DNM_NO_EXPLICIT_KERNEL") == nullptr) {
+    const i64 blocks = (M + EX_ROWS - 1) / EX_ROWS;
+    const int grid = (int)std::max<i64>(1, std::min<i64>(blocks, (i64)G.sm_count * 8));
+    k_mult_explicit<<<grid, EX_ROWS, 0, G.stream>>>(A->right.explicit_dev(), A->msc, A->d_diag, x, y, M);
+    count_launch();
+    DNM_CHECK_CUDA(cudaGetLastError());
+    return;
+  }
   with_sub(A->left, [&](auto ls) {
     with_sub(A->right, [&](auto rs) {
       k_mult_general<<<row_grid(M), TPB, 0, G.stream>>>(ls, rs, A->msc, A->d_diag, x, y, M);
@@ -361,6 +471,8 @@ extern "C" int dnm_mat_create(int64_t nmasks, const int64_t *masks, const int64_
   DNM_REQUIRE(A->left.desc.L == A->right.desc.L, DNM_ERR_ARG, "left and right subspaces have different L");
   A->M = A->left.dim;
   A->N = A->right.dim;
+  A->same_explicit = A->left.desc.type == DNM_EXPLICIT && A->right.desc.type == DNM_EXPLICIT &&
+                     A->left.state_map == A->right.state_map;
   if (xparity) {  // bcuda_template_2.cu:19-22
     DNM_REQUIRE(A->M % 2 == 0 && A->N % 2 == 0, DNM_ERR_ARG, "XParity needs even parent dimensions");
     A->M /= 2;

@@ -1202,9 +1202,11 @@ std::unique_ptr<TiledPlan> plan_with(dnm_mat_s *A, const std::vector<NMask> &mas
       }
     }
     if (plan->fold && !fold.empty()) plan->fold_failed = true;  // no lean pass could take the remote masks
-    // Spread the NVLink volume: a second lean pass evaluates the same folded masks on the other half of
-    // the rows (split by an index bit that lies outside both windows, i.e. per tile).
-    if (plan->fold && !plan->fold_failed && getenv("DNM_NO_FOLD_SPLIT") == nullptr) {
+    // Optional (DNM_FOLD_SPLIT=1): a second lean pass evaluates the same folded masks on the other half
+    // of the rows (split by an index bit outside both windows, i.e. per tile), which spreads the NVLink
+    // volume over two passes.  Measured at 2 GPUs (L=31): MBL 25.7 -> 26.0 ms, long_range 80 -> 90 ms --
+    // the extra operand buffers cost more resident CTAs than the balance gains, so it is off.
+    if (plan->fold && !plan->fold_failed && getenv("DNM_FOLD_SPLIT") != nullptr) {
       int ia = -1, ib = -1;
       for (size_t k = 0; k < plan->passes.size(); ++k)
         if (!plan->passes[k].src_fold.empty()) ia = (int)k;
