@@ -437,7 +437,7 @@ void gen_classic(Out &o, const PassDesc &pd, int index)
   o("    const i64 og = outer | rank_bits;  // index bits shared by the tile (signs)\n");
   o("    const i64 base = outer | %s;\n", deposit_expr("tid", pd.W, 0, g.LOG_NT).c_str());
   for (int r = 0; r < R; ++r) o("    cpa16(&tile[tid + %d], x + (base | 0x%llxll));\n", r * NT, (u64)g.roff[r]);
-  const int nrem = remote_groups(pd);
+  const int nrem = pd.stage_remote ? remote_groups(pd) : 0;
   if (nrem) {
     // operands of the folded remote masks: asynchronous copies from the partners' shards over NVLink into
     // their own buffers, in flight while the local masks are evaluated
@@ -798,7 +798,7 @@ Module *compile(const std::string &src, const std::vector<PassDesc> &passes, std
         kn.box[i] = bx.box[i];
       }
     } else {
-      kn.smem = ((size_t)16 << pd.T) * (size_t)(1 + remote_groups(pd));
+      kn.smem = ((size_t)16 << pd.T) * (size_t)(1 + (pd.stage_remote ? remote_groups(pd) : 0));
     }
     d.funcSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)kn.smem);
     d.funcSetAttribute(f, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100);

@@ -57,6 +57,9 @@ struct PassDesc {
   std::vector<int> W;  // window positions, W[j] = index bit of window coordinate j (ascending)
   // folded remote masks only on the tiles whose index bit filter_bit equals filter_val (-1: all tiles)
   int filter_bit = -1, filter_val = 0;
+  // folded remote operands: false = loaded straight into registers inside the group, true = staged by
+  // cp.async in shared-memory buffers of their own (classic kernels)
+  bool stage_remote = false;
   // shape of the generated kernel
   bool pipelined = false;
   int rows = 8;  // rows per thread (4 or 8)

@@ -753,6 +753,11 @@ Pass make_pass(const std::vector<const NMask *> &masks, const std::vector<int> &
 }
 
 // Greedy window cover of one partner group's masks.
+// Folded remote operands: loaded straight into registers by default; DNM_REMOTE_STAGE=1 stages them with
+// cp.async in shared-memory buffers (one exposed NVLink round trip per tile, but fewer resident CTAs:
+// measured slower at 4 GPUs, 54 against 42 ms at L=32 MBL).
+bool stage_remote_operands() { return getenv("DNM_REMOTE_STAGE") && atoi(getenv("DNM_REMOTE_STAGE")) != 0; }
+
 // a mask the lean group loop can serve: at most two distinct sign masks per (real | imaginary) part
 bool pair_eligible(const NMask *nm)
 {
@@ -872,8 +877,9 @@ void plan_group(TiledPlan &plan, std::vector<const NMask *> remaining, int peer_
       // spread the NVLink volume over the passes: half of the remote masks here when another pass follows
       bool more_passes = false;
       for (size_t k = 0; k < remaining.size(); ++k) more_passes = more_passes || !taken[k];
-      (void)more_passes;
-      size_t take = fold->size();
+      // spread the NVLink volume: half of the remote masks here when another pass follows (measured at 4
+      // GPUs, L=32 MBL: 42 ms against 54 ms with every remote mask in the first pass)
+      size_t take = more_passes ? (fold->size() + 1) / 2 : fold->size();
       // every folded group stages its operand in a shared-memory buffer of its own next to the tile (one per
       // mask, two when its real and imaginary parts cannot share the fetch)
       {
@@ -888,7 +894,7 @@ void plan_group(TiledPlan &plan, std::vector<const NMask *> remaining, int peer_
           if (nre && nim && !(sre.size() == 1 && sim.size() == 1)) return 2;
           return 1;
         };
-        const size_t room = (size_t)(200 * 1024) / ((size_t)16 << T) - 1;
+        const size_t room = stage_remote_operands() ? (size_t)(200 * 1024) / ((size_t)16 << T) - 1 : (size_t)64;
         size_t used = 0, fit = 0;
         while (fit < take && used + buffers((*fold)[fit]) <= room) used += buffers((*fold)[fit++]);
         take = fit;
@@ -1411,6 +1417,7 @@ TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false, int tune = -1)
       d.T = ps.T;
       d.nloc = best->nloc;
       d.W = ps.W;
+      d.stage_remote = stage_remote_operands();
       d.filter_bit = ps.filter_bit;
       d.filter_val = ps.filter_val;
       d.rows = 8;
