@@ -358,8 +358,10 @@ def run_extras(level, world, lib, args, L_main):
         return out
 
     def timed(fn, warm=True):
-        # the first call also pays CUDA's lazy loading of every kernel variant; report the repeat
-        if warm:
+        # the first call pays CUDA's lazy loading of every kernel variant (and, for small problems, the
+        # allocations that keep the Krylov column out of a CUDA graph), the second the first graph
+        # instantiation: report the steady state
+        for _ in range(2 if warm else 0):
             fn()
         lib.dnm_synchronize()
         t0 = time.perf_counter()
@@ -604,7 +606,8 @@ def run_ours(args, rank, world, local_rank):
             traffic = json.load(f).get(f'{args.H}_L{L}_n{world}')
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': traffic, 'peak_source': peak_src,
-                'kernel': 'k_tiled (window-tiled MatMult), %d launches per MatMult' % int(passes),
+                'kernel': ('dnm_jit_p* (generated window-tiled passes, %d of %d launches per MatMult)' % (int(mat.get_info('jit_passes')), int(passes))
+                           if mat.get_info('jit_passes') else 'k_tiled (window-tiled MatMult), %d launches per MatMult' % int(passes)),
                 'algorithmic_bytes_per_matmult': model_bytes,
                 'compulsory_bytes_per_matmult': compulsory,
                 'compulsory_gbs': compulsory / (sec / args.steps) / 1e9,
@@ -612,7 +615,10 @@ def run_ours(args, rank, world, local_rank):
                 'dram_gbs': (traffic / (sec / args.steps) / 1e9) if traffic else None,
                 'dram_frac': (traffic / (sec / args.steps) / 1e9 / peak) if traffic else None,
                 'note': 'achieved uses the north-star model (unique_masks+1)*N*16 B per MatMult per GPU; the '
-                        'tiled kernel moves far fewer bytes than the model, so frac > 1 is expected'}
+                        'tiled kernel moves far fewer bytes than the model, so frac > 1 is expected; dram_frac = '
+                        'measured DRAM bytes (ncu, profiles/traffic.json) / time / peak is the roofline fraction of '
+                        'the memory system; e2e is PCIe-bound (2 x 16 GiB per product), only amortisation over '
+                        'several products per transfer (evolve, eigsolve) changes it'}
 
     # ---- CPU baseline beside it (rank 0, N=1): bounded sample reusing the pinned buffers ----
     cpu = None

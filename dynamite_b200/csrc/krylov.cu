@@ -421,7 +421,8 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
         if (ok && cudaGraphInstantiate(&graph_exec, graph, 0) != cudaSuccess) ok = false;
         if (graph) cudaGraphDestroy(graph);
         if (!ok) {
-          cudaGetLastError();
+          const cudaError_t why = cudaGetLastError();
+          if (trace.on) fprintf(stderr, "[dnm trace] evolve: graph capture failed (%s), launching directly\n", cudaGetErrorString(why));
           graph_exec = nullptr;
           graph_failed = true;
         }
