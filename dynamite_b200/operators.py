@@ -316,6 +316,25 @@ class Operator:
         result.set_initialized()
         return result
 
+    def create_states(self):
+        """(bra, ket): uninitialised states in this operator's left and right subspaces
+        (reference ``operators.py:760-773``)."""
+        from .states import State
+        self.establish_L()
+        return State(subspace=self.left_subspace), State(subspace=self.right_subspace)
+
+    def expectation(self, state, tmp_state=None):
+        """<state| A |state> as a float (operators here are Hermitian, so the imaginary part is
+        dropped; reference ``operators.py:775-796``).  The product and the inner product run on the
+        device -- only the final scalar crosses to the host -- so chains such as
+        ``A.expectation(H.evolve(psi, t))`` (the OTOC loops of examples/scripts/SYK/run_syk.py) never
+        move a state vector off the GPU.  ``tmp_state`` is optional scratch in the left subspace."""
+        if tmp_state is None:
+            tmp_state = self.dot(state)
+        else:
+            self.dot(state, result=tmp_state)
+        return state.dot(tmp_state).real
+
     def evolve(self, state, t, **kwargs):
         from .computations import evolve
         return evolve(self, state, t, **kwargs)

@@ -188,13 +188,24 @@ int dnm_mat_norm_inf(dnm_mat_t A, double *nrm);
 int dnm_mat_size(dnm_mat_t A, int64_t *M, int64_t *N);
 /* MATOP_DESTROY  _backend/bcuda_template_2.cu:110-139 */
 int dnm_mat_destroy(dnm_mat_t A);
-/* Tuning / introspection knobs.  keys: "kernel" (0 auto, 1 general gather,
- * 2 tiled window), "tile_bits" (0 auto, 8..13), "tile_rows" (0 auto, 8, 16),
- * "pipeline" (0 auto, 1 pipelined persistent tiled kernel, 2 one tile per CTA),
- * "verbose". */
+/* Tuning / introspection knobs.  keys:
+ *   "kernel"    0 auto, 1 general gather, 2 tiled window
+ *   "tile_bits" 0 auto, 8..13 (log2 of the tile held in shared memory)
+ *   "tile_rows" 0 auto, 8, 16 (rows per thread of the generic tiled kernel)
+ *   "far_bits"  -1 auto, 0..16: index positions outside the window a tiled pass may serve through
+ *               the L2 (FAR masks: operands read from global memory while the tiles of one
+ *               far-bit block are in flight together)
+ *   "jit"       -1 auto (on for >= 2^22 rows per GPU), 0 off, 1 on: operator-specialised pass
+ *               kernels generated as CUDA source and compiled with NVRTC for sm_100a
+ *   "pipeline"  generated kernels: 1 = persistent CTAs with a TMA (cp.async.bulk[.tensor]) +
+ *               mbarrier ring and a cp.reduce.async.bulk.tensor add epilogue; 0 / 2 = one tile
+ *               per CTA (default: measured faster)
+ *   "autotune"  -1 auto (on for >= 2^24 rows per GPU), 0 off, 1 on: the first MatMult times a
+ *               few plan shapes on the caller's vectors and keeps the fastest
+ *   "verbose"   plan / autotune messages on stderr */
 int dnm_mat_set_option(dnm_mat_t A, const char *key, int64_t value);
-/* keys: "kernel", "passes", "unique_masks", "nterms", "model_bytes",
- * "compulsory_bytes", "launches_per_mult" */
+/* keys: "kernel", "passes", "jit_passes" (passes running generated kernels), "tuned_shape",
+ * "unique_masks", "nterms", "model_bytes", "compulsory_bytes", "launches_per_mult", "has_diag" */
 int dnm_mat_get_info(dnm_mat_t A, const char *key, double *value);
 /* CheckConserves  _backend/bpetsc_template_2.c:990-1056 (bpetsc.pyx:150-193) */
 int dnm_check_conserves(int64_t nmasks, const int64_t *masks, const int64_t *mask_offsets,

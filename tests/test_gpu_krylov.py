@@ -305,3 +305,34 @@ def test_state_api_and_checkpoint(gpu, tmp_path):
     lhs = xp.convert_state(H.dot(sx))          # convert(H_x psi)
     rhs = H.dot(up)                            # H_parent convert(psi)
     assert np.allclose(lhs.to_numpy(), rhs.to_numpy(), atol=1e-13)
+
+
+def test_expectation_pipeline(gpu):
+    """Operator.expectation and an evolve -> expectation chain (reference operators.py:775-796,
+    examples/scripts/SYK/run_syk.py:179-206) against dense numpy."""
+    import scipy.linalg
+    from dynamite_b200 import msc_tools
+    from dynamite_b200.hamiltonians import build_hamiltonian
+    from dynamite_b200.states import State
+    from dynamite_b200.subspaces import Full
+    L = 8
+    H = build_hamiltonian('MBL', L)
+    W = build_hamiltonian('long_range', L)
+    for op in (H, W):
+        op.subspace = Full(L=L)
+    psi = State(L=L, state='random', seed=3)
+    v = psi.to_numpy()
+    full = oracle.Subspace({'type': 'full', 'L': L})
+    dense = {}
+    for name, op in (('H', H), ('W', W)):
+        op.reduce_msc()
+        dense[name] = msc_tools.msc_to_numpy(op.msc, (256, 256), full.i2s, full.s2i)
+    assert abs(H.expectation(psi) - np.vdot(v, dense['H'] @ v).real) < 1e-12
+    tmp = State(L=L)
+    assert abs(W.expectation(psi, tmp_state=tmp) - np.vdot(v, dense['W'] @ v).real) < 1e-12
+    t = 0.7
+    got = W.expectation(H.evolve(psi, t, tol=1e-12))
+    vt = scipy.linalg.expm(-1j * t * dense['H']) @ v
+    assert abs(got - np.vdot(vt, dense['W'] @ vt).real) < 1e-10
+    bra, ket = H.create_states()
+    assert bra.subspace == H.left_subspace and ket.subspace == H.right_subspace
