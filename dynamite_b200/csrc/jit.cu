@@ -205,7 +205,9 @@ int remote_groups(const PassDesc &pd)
 // 1: emit ONLY the asynchronous copies (cp.async, peer memory -> shared buffer k of the pass) of the
 //    remote groups, under the same activity conditions as the arithmetic; 2: every group, the remote
 //    ones reading their shared buffer (NVLink latency is then paid once per tile, behind the local work)
-void gen_groups(Out &o, const PassDesc &pd, const Geo &g_, int remote_mode = 0)
+// select 0: every group; 1: only the FAR groups (operands from global memory: they do not need the
+// staged tile); 2: only the groups served from the tile
+void gen_groups(Out &o, const PassDesc &pd, const Geo &g_, int remote_mode = 0, int select = 0)
 {
   int remote_index = -1;
   const PassParams &P = *pd.p;
@@ -239,6 +241,7 @@ void gen_groups(Out &o, const PassDesc &pd, const Geo &g_, int remote_mode = 0)
       const int gi = g + 1;
       ++g;
       if (remote_mode == 1 && !remote_m) continue;
+      if ((select == 1 && !G.far) || (select == 2 && G.far)) continue;
       const bool issue_m = remote_mode == 1, staged_m = remote_mode == 2 && remote_m;
       if (staged_m && remote_index == 0) o("    cpa_wait_all();  // the staged remote operands (each thread reads back only what it copied)\n");
       const double cr = S.cf[2 * (gi - 1)], ci = S.cf[2 * gi];
@@ -303,6 +306,7 @@ void gen_groups(Out &o, const PassDesc &pd, const Geo &g_, int remote_mode = 0)
     const bool remote = G.far && G.peer != 0;
     if (remote) ++remote_index;
     if (remote_mode == 1 && !remote) continue;
+    if ((select == 1 && !G.far) || (select == 2 && G.far)) continue;
     const bool issue = remote_mode == 1, staged = remote_mode == 2 && remote;
     if (staged && remote_index == 0) o("    cpa_wait_all();  // the staged remote operands (each thread reads back only what it copied)\n");
 
@@ -450,12 +454,27 @@ void gen_classic(Out &o, const PassDesc &pd, int index)
   o("    if (diag != nullptr) {\n");
   for (int r = 0; r < R; ++r) o("      dg%d = %s(diag + (base | 0x%llxll));\n", r, hint_ld(), (u64)g.roff[r]);
   o("    }\n");
-  if (nrem) o("    cpa_wait_first();\n    __syncthreads();\n");
-  else o("    cpa_wait();\n    __syncthreads();\n");
-  o("%s", acc_decl(R).c_str());
-  for (int r = 0; r < R; ++r)
-    o("    { const double2 v = tile[tid + %d]; ar%d = dg%d * v.x; ai%d = dg%d * v.y; }\n", r * NT, r, r, r, r);
-  gen_groups(o, pd, g, nrem ? 2 : 0);
+  // experiment (DNM_JIT_FAR_FIRST=1): measured slower, 20.6 against 18.1 ms at L=30 MBL -- the far loads then
+  // miss the L2 more often because they run ahead of the partner tiles' own staging
+  const bool far_first = !nrem && getenv("DNM_JIT_FAR_FIRST") && atoi(getenv("DNM_JIT_FAR_FIRST")) != 0;
+  if (far_first) {
+    // the FAR groups read global memory only: they run while the tile is still in flight
+    o("%s", acc_decl(R).c_str());
+    for (int r = 0; r < R; ++r) o("    ar%d = 0.0; ai%d = 0.0;\n", r, r);
+    o("    cpa_commit();\n");
+    gen_groups(o, pd, g, 0, 1);
+    o("    cpa_wait_all();\n    __syncthreads();\n");
+    for (int r = 0; r < R; ++r)
+      o("    { const double2 v = tile[tid + %d]; ar%d = fma(dg%d, v.x, ar%d); ai%d = fma(dg%d, v.y, ai%d); }\n", r * NT, r, r, r, r, r, r);
+    gen_groups(o, pd, g, 0, 2);
+  } else {
+    if (nrem) o("    cpa_wait_first();\n    __syncthreads();\n");
+    else o("    cpa_wait();\n    __syncthreads();\n");
+    o("%s", acc_decl(R).c_str());
+    for (int r = 0; r < R; ++r)
+      o("    { const double2 v = tile[tid + %d]; ar%d = dg%d * v.x; ai%d = dg%d * v.y; }\n", r * NT, r, r, r, r);
+    gen_groups(o, pd, g, nrem ? 2 : 0);
+  }
   if (P.accumulate == 1) {
     o("    __syncthreads();\n");
     for (int r = 0; r < R; ++r) o("    cpa16(&tile[tid + %d], y + (base | 0x%llxll));\n", r * NT, (u64)g.roff[r]);
