@@ -343,13 +343,14 @@ void gen_groups(Out &o, const PassDesc &pd, const Geo &g_, int remote_mode = 0, 
       return buf;
     };
     auto emit_rows = [&](const std::vector<int> &rows, const char *cv, const char *indent) {
+      const size_t chunk = (G.far && getenv("DNM_JIT_FAR_CHUNK")) ? (size_t)std::max(1, atoi(getenv("DNM_JIT_FAR_CHUNK"))) : 4;
       if (issue) {
         for (int r : rows)
           o("%scpa16(&tile[%d + tid + %d], src + 0x%llxll);\n", indent, (1 + remote_index) << g_.T, r * NT, (u64)g_.roff[r ^ HI]);
         return;
       }
-      for (size_t h = 0; h < rows.size(); h += 4) {
-        const size_t e = std::min(rows.size(), h + 4);
+      for (size_t h = 0; h < rows.size(); h += chunk) {
+        const size_t e = std::min(rows.size(), h + chunk);
         o("%s{\n", indent);
         for (size_t k = h; k < e; ++k) o("%s  const double2 v%d = %s;\n", indent, rows[k], operand(rows[k]).c_str());
         for (size_t k = h; k < e; ++k) {
@@ -426,7 +427,8 @@ void gen_classic(Out &o, const PassDesc &pd, int index)
   const PassParams &P = *pd.p;
   const Geo g(pd);
   const int R = g.R, NT = g.NT;
-  const int minb = std::max(1, std::min(8, 65536 / (NT * 64)));
+  int minb = std::max(1, std::min(8, 65536 / (NT * 64)));
+  if (getenv("DNM_JIT_MINB")) minb = std::max(1, std::min(minb, atoi(getenv("DNM_JIT_MINB"))));
   o("// ---- pass %d (classic): T=%d R=%d, %d groups, %s, far_bits=%d\n", index, g.T, R, P.ngroups,
     P.accumulate ? "accumulate" : "write", P.far_bits);
   o("extern \"C\" __global__ void __launch_bounds__(%d, %d)\n", NT, minb);

@@ -1439,7 +1439,9 @@ TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false, int tune = -1)
       std::string log;
       const std::string src = jit::generate(descs);
       if (const char *dump = getenv("DNM_JIT_DUMP")) {
-        if (FILE *f = fopen(dump, "w")) {
+        // (autotuner trials go to <file>.shape<k>; dnm_mat_get_info "tuned_shape" names the one that was kept)
+        const std::string path = tune >= 0 ? std::string(dump) + ".shape" + std::to_string(tune) : std::string(dump);
+        if (FILE *f = fopen(path.c_str(), "w")) {
           fwrite(src.data(), 1, src.size(), f);
           fclose(f);
         }
