@@ -111,7 +111,13 @@ def compute_rcm(masks, signs, coeffs, state_map, start, L):
     if not (state_map.dtype == np.int64 and state_map.flags.c_contiguous):
         raise ValueError('state_map must be a contiguous int64 array')
     out = C.c_int64()
-    ierr = _capi.lib().dnm_compute_rcm(masks.size, ip(masks), ip(signs),
+    # big searches run on the GPU when one is initialised (same output, element for element);
+    # DNM_RCM_DEVICE=0 / 1 forces the host / device version
+    import os
+    where = os.environ.get('DNM_RCM_DEVICE')
+    on_device = _capi.lib().dnm_have_gpu() and (where == '1' or (where != '0' and state_map.size >= (1 << 16)))
+    fn = _capi.lib().dnm_compute_rcm_device if on_device else _capi.lib().dnm_compute_rcm
+    ierr = fn(masks.size, ip(masks), ip(signs),
                                        _capi.fp(coeffs), ip(state_map), state_map.size,
                                        int(start), int(L), C.byref(out))
     if ierr:

@@ -129,6 +129,11 @@ int dnm_subspace_i2s(const dnm_subspace_t *s, int64_t n, const int64_t *idxs, in
 int dnm_compute_rcm(int64_t nterms, const int64_t *masks, const int64_t *signs,
                     const double *coeffs, int64_t *state_map, int64_t max_states,
                     int64_t start, int64_t L, int64_t *dim_out);
+/* The same search on the device (frontier expansion with a hash table of first-discovery keys,
+ * csrc/rcm.cu): identical output, element for element.  Needs dnm_init. */
+int dnm_compute_rcm_device(int64_t nterms, const int64_t *masks, const int64_t *signs,
+                           const double *coeffs, int64_t *state_map, int64_t max_states,
+                           int64_t start, int64_t L, int64_t *dim_out);
 /* The same maps evaluated by the device functions the kernels use (for the
  * bit-exact device-vs-oracle parity tests).  Host arrays in, host arrays out. */
 int dnm_subspace_s2i_device(const dnm_subspace_t *s, int64_t n, const int64_t *states, int64_t *idxs);

@@ -326,7 +326,8 @@ def test_expectation_pipeline(gpu):
     dense = {}
     for name, op in (('H', H), ('W', W)):
         op.reduce_msc()
-        dense[name] = msc_tools.msc_to_numpy(op.msc, (256, 256), full.i2s, full.s2i)
+        A = msc_tools.msc_to_numpy(op.msc, (256, 256), full.i2s, full.s2i)
+        dense[name] = np.asarray(A.todense() if hasattr(A, 'todense') else A, dtype=np.complex128)
     assert abs(H.expectation(psi) - np.vdot(v, dense['H'] @ v).real) < 1e-12
     tmp = State(L=L)
     assert abs(W.expectation(psi, tmp_state=tmp) - np.vdot(v, dense['W'] @ v).real) < 1e-12
@@ -336,3 +337,36 @@ def test_expectation_pipeline(gpu):
     assert abs(got - np.vdot(vt, dense['W'] @ vt).real) < 1e-10
     bra, ket = H.create_states()
     assert bra.subspace == H.left_subspace and ket.subspace == H.right_subspace
+
+
+@pytest.mark.parametrize('name,L,start', [('heisenberg', 16, 0b0101010101010101), ('XX', 14, 0b111), ('SYK', 7, 0),
+                                          ('long_range', 10, 5), ('heisenberg', 22, (1 << 11) - 1)])
+def test_compute_rcm_device(gpu, name, L, start):
+    """Auto-subspace search on the device (csrc/rcm.cu) against the host port of the reference's queue
+    walk (bsubspace.pyx:212-261): the same states in the same order, and the same size error."""
+    import ctypes as C
+    from dynamite_b200 import _capi
+    from dynamite_b200.hamiltonians import build_hamiltonian
+    H = build_hamiltonian(name, L)
+    H.reduce_msc()
+    masks = np.ascontiguousarray(H.msc['masks'], dtype=np.int64)
+    signs = np.ascontiguousarray(H.msc['signs'], dtype=np.int64)
+    coeffs = np.ascontiguousarray(H.msc['coeffs'], dtype=np.complex128)
+    lib = _capi.lib()
+
+    def run(fn, cap):
+        out = np.full(cap, -7, dtype=np.int64)
+        dim = C.c_int64()
+        rc = fn(masks.size, _capi.ip(masks), _capi.ip(signs), _capi.fp(coeffs), _capi.ip(out), cap, int(start), L,
+                C.byref(dim))
+        return rc, dim.value, out
+
+    cap = 1 << min(L, 21)
+    rc_h, dim_h, host = run(lib.dnm_compute_rcm, cap)
+    rc_d, dim_d, dev = run(lib.dnm_compute_rcm_device, cap)
+    assert rc_h == 0 and rc_d == 0 and dim_h == dim_d and dim_h > 1
+    assert np.array_equal(host[:dim_h], dev[:dim_d])
+    if dim_h > 4:
+        rc_h, _, _ = run(lib.dnm_compute_rcm, dim_h - 3)
+        rc_d, _, _ = run(lib.dnm_compute_rcm_device, dim_h - 3)
+        assert rc_h != 0 and rc_d != 0          # 'state_map size too small' from both
