@@ -421,7 +421,9 @@ std::string acc_decl(int R)
   return s + ";\n";
 }
 
-// one tile per CTA, cp.async staging
+void emit_tma_helpers(Out &o, const PassDesc &pd, int index, const Box &bx, bool reduce);
+
+// one tile per CTA; the tile is staged by cp.async (any window) or by TMA (window = a tensor box)
 void gen_classic(Out &o, const PassDesc &pd, int index)
 {
   const PassParams &P = *pd.p;
@@ -429,21 +431,44 @@ void gen_classic(Out &o, const PassDesc &pd, int index)
   const int R = g.R, NT = g.NT;
   int minb = std::max(1, std::min(8, 65536 / (NT * 64)));
   if (getenv("DNM_JIT_MINB")) minb = std::max(1, std::min(minb, atoi(getenv("DNM_JIT_MINB"))));
-  o("// ---- pass %d (classic): T=%d R=%d, %d groups, %s, far_bits=%d\n", index, g.T, R, P.ngroups,
+  const int nrem = pd.stage_remote ? remote_groups(pd) : 0;
+  const bool tma = pd.tma_stage;
+  const bool tma_reduce = tma && pd.tma_reduce && P.accumulate == 1;
+  const Box bx = tile_box(pd);
+  o("// ---- pass %d (classic%s): T=%d R=%d, %d groups, %s, far_bits=%d\n", index, tma ? ", TMA staging" : "", g.T, R, P.ngroups,
     P.accumulate ? "accumulate" : "write", P.far_bits);
+  if (tma) emit_tma_helpers(o, pd, index, bx, tma_reduce);
   o("extern \"C\" __global__ void __launch_bounds__(%d, %d)\n", NT, minb);
-  o("dnm_jit_p%d(const double2 *__restrict__ x, double2 *__restrict__ y, const double *__restrict__ diag, i64 rank_bits,\n"
-    "           const __grid_constant__ Peers xs)\n{\n",
-    index);
-  o("  extern __shared__ double2 tile[];\n");
+  if (tma)
+    o("dnm_jit_p%d(const __grid_constant__ TMap tmx, const __grid_constant__ TMap tmy, const double2 *__restrict__ x,\n"
+      "           double2 *__restrict__ y, const double *__restrict__ diag, i64 rank_bits, u64 ntiles,\n"
+      "           const __grid_constant__ Peers xs)\n{\n",
+      index);
+  else
+    o("dnm_jit_p%d(const double2 *__restrict__ x, double2 *__restrict__ y, const double *__restrict__ diag, i64 rank_bits,\n"
+      "           const __grid_constant__ Peers xs)\n{\n",
+      index);
+  if (tma) {
+    o("  extern __shared__ __align__(1024) unsigned char smem[];\n");
+    o("  double2 *tile = reinterpret_cast<double2 *>(smem);\n");
+    o("  u64 *bar = reinterpret_cast<u64 *>(smem + %zu);\n", ((size_t)16 << g.T) * (size_t)(1 + nrem));
+  } else {
+    o("  extern __shared__ double2 tile[];\n");
+  }
   o("  const u32 tid = threadIdx.x;\n");
   o("  const u64 tb = blockIdx.x;\n");
+  if (tma) {
+    // one elected thread stages the whole tile: cp.async.bulk[.tensor] completes on the mbarrier
+    o("  if (tid == 0) {\n    mbar_init(bar, 1);\n    asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\");\n  }\n");
+    o("  __syncthreads();\n");
+    o("  if (tid == 0) load_p%d(&tmx, x, tb, tile, bar);\n", index);
+  }
   o("  {\n");
   o("    const i64 outer = (i64)(%s);\n", outer_expr(P, "tb").c_str());
   o("    const i64 og = outer | rank_bits;  // index bits shared by the tile (signs)\n");
   o("    const i64 base = outer | %s;\n", deposit_expr("tid", pd.W, 0, g.LOG_NT).c_str());
-  for (int r = 0; r < R; ++r) o("    cpa16(&tile[tid + %d], x + (base | 0x%llxll));\n", r * NT, (u64)g.roff[r]);
-  const int nrem = pd.stage_remote ? remote_groups(pd) : 0;
+  if (!tma)
+    for (int r = 0; r < R; ++r) o("    cpa16(&tile[tid + %d], x + (base | 0x%llxll));\n", r * NT, (u64)g.roff[r]);
   if (nrem) {
     // operands of the folded remote masks: asynchronous copies from the partners' shards over NVLink into
     // their own buffers, in flight while the local masks are evaluated
@@ -465,19 +490,30 @@ void gen_classic(Out &o, const PassDesc &pd, int index)
     for (int r = 0; r < R; ++r) o("    ar%d = 0.0; ai%d = 0.0;\n", r, r);
     o("    cpa_commit();\n");
     gen_groups(o, pd, g, 0, 1);
-    o("    cpa_wait_all();\n    __syncthreads();\n");
+    if (tma) o("    mbar_wait(bar, 0);\n");
+    else o("    cpa_wait_all();\n    __syncthreads();\n");
     for (int r = 0; r < R; ++r)
       o("    { const double2 v = tile[tid + %d]; ar%d = fma(dg%d, v.x, ar%d); ai%d = fma(dg%d, v.y, ai%d); }\n", r * NT, r, r, r, r, r, r);
     gen_groups(o, pd, g, 0, 2);
   } else {
-    if (nrem) o("    cpa_wait_first();\n    __syncthreads();\n");
+    if (tma) o("    mbar_wait(bar, 0);\n");
+    else if (nrem) o("    cpa_wait_first();\n    __syncthreads();\n");
     else o("    cpa_wait();\n    __syncthreads();\n");
     o("%s", acc_decl(R).c_str());
     for (int r = 0; r < R; ++r)
       o("    { const double2 v = tile[tid + %d]; ar%d = dg%d * v.x; ai%d = dg%d * v.y; }\n", r * NT, r, r, r, r);
     gen_groups(o, pd, g, nrem ? 2 : 0);
   }
-  if (P.accumulate == 1) {
+  if (tma_reduce) {
+    // the result tile goes through shared memory and is ADDED into y by the TMA unit: the old y never
+    // enters the SM
+    o("    __syncthreads();  // nobody reads the operand tile any more\n");
+    for (int r = 0; r < R; ++r) o("    tile[tid + %d] = make_double2(ar%d, ai%d);\n", r * NT, r, r);
+    o("    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n");
+    o("    __syncthreads();\n");
+    o("    if (tid == 0) {\n      reduce_p%d(&tmy, tb, tile);\n", index);
+    o("      asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");  // shared memory must outlive the read\n    }\n");
+  } else if (P.accumulate == 1) {
     o("    __syncthreads();\n");
     for (int r = 0; r < R; ++r) o("    cpa16(&tile[tid + %d], y + (base | 0x%llxll));\n", r * NT, (u64)g.roff[r]);
     o("    cpa_wait();\n");
@@ -499,18 +535,12 @@ int pipelined_ctas(const PassDesc &pd)
   return std::max(1, std::min(std::min(by_smem, by_threads), 4));
 }
 
-// persistent CTAs, TMA ring, reduce-add epilogue
-void gen_pipelined(Out &o, const PassDesc &pd, int index)
+// outer_p<k>(tile) = index bits outside the window; load_p<k> = TMA load of a tile into shared memory
+// (signals `bar`); reduce_p<k> = cp.reduce.async.bulk.tensor add of a result tile into y
+void emit_tma_helpers(Out &o, const PassDesc &pd, int index, const Box &bx, bool reduce)
 {
   const PassParams &P = *pd.p;
-  const Geo g(pd);
-  const Box bx = tile_box(pd);
-  const int R = g.R, NT = g.NT, T = g.T;
-  const bool reduce = P.accumulate == 1;
-  const int ctas = pipelined_ctas(pd);
-  const u32 tile_bytes = 16u << T;
-  o("// ---- pass %d (pipelined): T=%d R=%d nbuf=%d, %d groups, %s, far_bits=%d, TMA rank %d\n", index, T, R, pd.nbuf, P.ngroups,
-    reduce ? "accumulate (reduce-add)" : "write", P.far_bits, bx.rank);
+  const u32 tile_bytes = 16u << pd.T;
   o("__device__ __forceinline__ i64 outer_p%d(u64 tb) { return (i64)(%s); }\n", index, outer_expr(P, "tb").c_str());
   auto coords = [&]() -> std::string {
     std::string c;
@@ -564,6 +594,21 @@ void gen_pipelined(Out &o, const PassDesc &pd, int index)
     o("  asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");\n}\n");
   }
 
+}
+
+// persistent CTAs, TMA ring, reduce-add epilogue
+void gen_pipelined(Out &o, const PassDesc &pd, int index)
+{
+  const PassParams &P = *pd.p;
+  const Geo g(pd);
+  const Box bx = tile_box(pd);
+  const int R = g.R, NT = g.NT, T = g.T;
+  const bool reduce = P.accumulate == 1;
+  const int ctas = pipelined_ctas(pd);
+  const u32 tile_bytes = 16u << T;
+  o("// ---- pass %d (pipelined): T=%d R=%d nbuf=%d, %d groups, %s, far_bits=%d, TMA rank %d\n", index, T, R, pd.nbuf, P.ngroups,
+    reduce ? "accumulate (reduce-add)" : "write", P.far_bits, bx.rank);
+  emit_tma_helpers(o, pd, index, bx, reduce);
   o("extern \"C\" __global__ void __launch_bounds__(%d, %d)\n", NT, ctas);
   o("dnm_jit_p%d(const __grid_constant__ TMap tmx, const __grid_constant__ TMap tmy, const double2 *__restrict__ x,\n"
     "           double2 *__restrict__ y, const double *__restrict__ diag, i64 rank_bits, u64 ntiles,\n"
@@ -820,6 +865,18 @@ Module *compile(const std::string &src, const std::vector<PassDesc> &passes, std
       }
     } else {
       kn.smem = ((size_t)16 << pd.T) * (size_t)(1 + (pd.stage_remote ? remote_groups(pd) : 0));
+      if (pd.tma_stage) {
+        const Box bx = tile_box(pd);
+        kn.tma_args = true;
+        kn.smem += 64;
+        kn.reduce = pd.tma_reduce && pd.p->accumulate == 1;
+        kn.rank = bx.rank;
+        for (int i = 0; i < bx.rank; ++i) {
+          kn.dims[i] = bx.dims[i];
+          kn.strides[i] = bx.strides[i];
+          kn.box[i] = bx.box[i];
+        }
+      }
     }
     d.funcSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)kn.smem);
     d.funcSetAttribute(f, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100);
@@ -875,11 +932,12 @@ void launch(const Kernel &k, unsigned long long ntiles, int sm_count, cudaStream
     const cplx *p[MAX_RANKS];
   } xs;
   for (int h = 0; h < MAX_RANKS; ++h) xs.p[h] = peers ? peers[h] : nullptr;
-  if (k.pipelined) {
+  if (k.pipelined || k.tma_args) {
     static const CUtensorMap zero = {};
     const CUtensorMap *tmx = k.rank > 0 ? tensor_map(k, x) : &zero;
     const CUtensorMap *tmy = (k.rank > 0 && k.reduce) ? tensor_map(k, y) : &zero;
-    const unsigned grid = (unsigned)std::min<unsigned long long>(ntiles, (unsigned long long)sm_count * k.ctas_per_sm);
+    const unsigned grid = k.pipelined ? (unsigned)std::min<unsigned long long>(ntiles, (unsigned long long)sm_count * k.ctas_per_sm)
+                                      : (unsigned)ntiles;
     void *args[] = {(void *)tmx, (void *)tmy, (void *)&x, (void *)&y, (void *)&diag, (void *)&rank_bits, (void *)&ntiles,
                     (void *)&xs};
     rc = driver().launchKernel((CUfunction)k.func, grid, 1, 1, (unsigned)k.threads, 1, 1, (unsigned)k.smem, (CUstream)stream, args,

@@ -34,6 +34,7 @@ struct Kernel {
   int threads = 0;
   // pipelined kernels
   bool pipelined = false;
+  bool tma_args = false;  // one tile per CTA, but the tile is staged by TMA (tensor-map kernel signature)
   int ctas_per_sm = 1;
   int rank = 0;  // tensor rank of the tile box, 0: contiguous tile (1-D bulk copy, no tensor map)
   unsigned long long dims[MAX_TMA_RANK] = {0}, strides[MAX_TMA_RANK] = {0};  // strides in bytes, [0] unused
@@ -60,6 +61,10 @@ struct PassDesc {
   // folded remote operands: false = loaded straight into registers inside the group, true = staged by
   // cp.async in shared-memory buffers of their own (classic kernels)
   bool stage_remote = false;
+  // one tile per CTA: the tile is staged by one elected thread with cp.async.bulk[.tensor] + mbarrier
+  // instead of eight cp.async per thread; tma_reduce: accumulating passes add their result tile into y
+  // with cp.reduce.async.bulk.tensor instead of fetching the old y
+  bool tma_stage = false, tma_reduce = false;
   // shape of the generated kernel
   bool pipelined = false;
   int rows = 8;  // rows per thread (4 or 8)

@@ -1418,6 +1418,11 @@ TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false, int tune = -1)
       d.nloc = best->nloc;
       d.W = ps.W;
       d.stage_remote = stage_remote_operands();
+      d.tma_stage = jit::tma_eligible(d) && (ps.peer_xor == 0 || best->dma) &&
+                    !(getenv("DNM_JIT_TMA") && atoi(getenv("DNM_JIT_TMA")) == 0);
+      // measured at L=30 MBL (same call): cp.async staging 18.4 ms, TMA staging 18.6 ms, TMA staging + reduce-add
+      // epilogue 17.8 ms -> both on by default (DNM_JIT_TMA=0 / DNM_JIT_TMA_REDUCE=0 turn them off)
+      d.tma_reduce = !(getenv("DNM_JIT_TMA_REDUCE") && atoi(getenv("DNM_JIT_TMA_REDUCE")) == 0);
       d.filter_bit = ps.filter_bit;
       d.filter_val = ps.filter_val;
       d.rows = 8;
