@@ -358,9 +358,8 @@ def run_extras(level, world, lib, args, L_main):
         return out
 
     def timed(fn, warm=True):
-        # the first call pays CUDA's lazy loading of every kernel variant (and, for small problems, the
-        # allocations that keep the Krylov column out of a CUDA graph), the second the first graph
-        # instantiation: report the steady state
+        # the first call pays CUDA's lazy loading of every kernel variant and the workspace allocations:
+        # report the steady state
         for _ in range(2 if warm else 0):
             fn()
         lib.dnm_synchronize()

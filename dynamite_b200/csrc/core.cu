@@ -64,9 +64,13 @@ dnm_vec_t pool_acquire(int64_t global_n)
 void pool_release(dnm_vec_t v)
 {
   if (!v) return;
-  // keep at most a quarter of the device memory parked in the pool
-  size_t f = 0, t = 0;
-  cudaMemGetInfo(&f, &t);
+  // keep at most a quarter of the device memory parked in the pool (the total is queried once:
+  // cudaMemGetInfo costs milliseconds on some drivers and a Krylov solve releases dozens of vectors)
+  static size_t t = 0;
+  if (t == 0) {
+    size_t f = 0;
+    cudaMemGetInfo(&f, &t);
+  }
   size_t pooled = 0;
   for (dnm_vec_t q : g_pool) pooled += sizeof(cplx) * (size_t)q->local_n;
   if (pooled + sizeof(cplx) * (size_t)v->local_n > t / 4 || g_pool.size() >= 256) {

@@ -369,7 +369,11 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
   // classical Gram-Schmidt + DGKS refinement)
   const char *orth_env = getenv("DNM_EVOLVE_ORTH");
   const bool lanczos = !(orth_env && !strcmp(orth_env, "full"));
-  bool use_graph = G.nranks == 1 && nloc <= ((int64_t)1 << 24) && getenv("DNM_NO_GRAPH") == nullptr;
+  // CUDA-graph capture of the basis construction: opt-in (DNM_EVOLVE_GRAPH=1).  Measured on C1 (L=20,
+  // scripts/explore_c1.py): once pool_release stopped calling cudaMemGetInfo per vector the plain launch
+  // sequence takes 4.7 ms per evolve, while capturing + instantiating a graph per call costs 5-70 ms.
+  bool use_graph = G.nranks == 1 && nloc <= ((int64_t)1 << 24) && getenv("DNM_EVOLVE_GRAPH") != nullptr &&
+                   getenv("DNM_NO_GRAPH") == nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_failed = false;
   struct GraphGuard {
@@ -406,8 +410,8 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
       // pinned staging (pageable targets cannot be captured); the front of h_scratch belongs to fetch_doubles
       DNM_CHECK_CUDA(cudaMemcpyAsync(G.h_scratch + 4096, d_H, hbytes, cudaMemcpyDeviceToHost, G.stream));
     };
-    // Small problems are launch-bound (C1: 0.36 ms per column against a 0.027 ms MatMult): the whole
-    // basis construction of a sub-step is a fixed launch sequence, captured once as a CUDA graph
+    // (opt-in) the whole basis construction of a sub-step is a fixed launch sequence: captured once per
+    // call as a CUDA graph
     if (use_graph && !graph_exec && !graph_failed) {
       cudaGraph_t graph = nullptr;
       if (cudaStreamBeginCapture(G.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
