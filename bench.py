@@ -269,7 +269,9 @@ def host_x_factors(n):
         return _FACTORS[n]
     rs = np.random.RandomState(1234)
     base = (rs.standard_normal(XP) + 1j * rs.standard_normal(XP)) / math.sqrt(2.0 * n)
-    w = np.exp(2j * np.pi * rs.random_sample(max(1, n // XP)))
+    # the high factor is a signed power of two: base * w is then exact, so every way of forming a slice of
+    # x (vectorised fill, per-window evaluation) gives the same bits
+    w = rs.choice(np.array([1.0, -1.0, 0.5, -0.5, 2.0, -2.0, 0.25, -0.25]), size=max(1, n // XP))
     _FACTORS[n] = (base, w)
     return base, w
 

@@ -77,6 +77,7 @@ _SIGNATURES = {
     'dnm_vec_device_ptr': (C.c_void_p, [_vec]),
     'dnm_vec_set_host': (C.c_int, [_vec, C.c_int64, C.c_int64, f64p]),
     'dnm_vec_get_host': (C.c_int, [_vec, C.c_int64, C.c_int64, f64p]),
+    'dnm_vec_get_host_global': (C.c_int, [_vec, C.c_int64, C.c_int64, f64p]),
     'dnm_vec_set_values': (C.c_int, [_vec, C.c_int64, i64p, f64p, C.c_int]),
     'dnm_vec_get_values': (C.c_int, [_vec, C.c_int64, i64p, f64p]),
     'dnm_vec_set': (C.c_int, [_vec, C.c_double, C.c_double]),

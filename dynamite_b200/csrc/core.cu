@@ -605,6 +605,31 @@ extern "C" int dnm_vec_get_host(dnm_vec_t v, int64_t offset, int64_t count, doub
   DNM_API_END
 }
 
+// Any contiguous range of the GLOBAL vector, read through the peer mappings of the other ranks'
+// shards (State.to_numpy on sharded vectors).  The caller synchronises the ranks first (Comm.barrier).
+extern "C" int dnm_vec_get_host_global(dnm_vec_t v, int64_t offset, int64_t count, double *values)
+{
+  DNM_API_BEGIN
+  require_init();
+  DNM_REQUIRE(v && values && offset >= 0 && count >= 0 && offset + count <= v->global_n, DNM_ERR_ARG,
+              "bad range [%lld, %lld) for global size %lld", (long long)offset, (long long)(offset + count),
+              (long long)(v ? v->global_n : 0));
+  const int64_t per = v->local_n;
+  int64_t done = 0;
+  while (done < count) {
+    const int64_t g = offset + done;
+    const int r = (int)(g / per);
+    const int64_t lo = g - (int64_t)r * per;
+    const int64_t n = std::min<int64_t>(count - done, per - lo);
+    const cplx *src = (G.nranks == 1 || r == G.rank) ? v->d : v->peer[r];
+    DNM_REQUIRE(src != nullptr, DNM_ERR_COMM, "vector is not mapped on rank %d", r);
+    DNM_CHECK_CUDA(cudaMemcpyAsync(values + 2 * done, src + lo, sizeof(cplx) * n, cudaMemcpyDeviceToHost, G.stream));
+    done += n;
+  }
+  DNM_CHECK_CUDA(cudaStreamSynchronize(G.stream));
+  DNM_API_END
+}
+
 namespace {
 __global__ void k_scatter_set(cplx *v, int64_t count, const int64_t *idx, const cplx *vals, int add)
 {

@@ -178,9 +178,20 @@ class State:
 
     # ---- host copies ---------------------------------------------------------------
     def to_numpy(self, to_all=False):
-        """the local block as a numpy array (the whole vector on one rank)"""
+        """The state as a numpy array (reference ``states.py:703-740``): on one rank the whole vector.
+        Sharded: with ``to_all`` every rank gets the whole vector (each rank's block is read through the
+        peer mappings of the Vec), otherwise rank 0 gets it and the other ranks get ``None``."""
         self.assert_initialized()
-        return self.vec.getArray()
+        if COMM_WORLD.size == 1:
+            return self.vec.getArray()
+        from . import _capi
+        COMM_WORLD.barrier()       # every rank's block is complete
+        full = None
+        if to_all or COMM_WORLD.rank == 0:
+            full = np.empty(len(self), dtype=np.complex128)
+            _capi.check(_capi.lib().dnm_vec_get_host_global(self.vec.handle, 0, full.size, _capi.fp(full)))
+        COMM_WORLD.barrier()       # nobody changes its block while others still read it
+        return full
 
     # ---- checkpoint / resume ---------------------------------------------------------
     _VEC_CLASSID = 1211214   # PETSc VEC_FILE_CLASSID

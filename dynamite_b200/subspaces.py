@@ -340,8 +340,13 @@ class XParity(Subspace):
     def convert_state(self, state):
         """XParity <-> parent conversion (reference ``subspaces.py:676-762``), done
         through host copies of the local blocks."""
+        from .petsc import COMM_WORLD
         from .states import State
         state.assert_initialized()
+        if COMM_WORLD.size > 1:
+            # the conversion pairs index i with the index of the globally flipped state, which lives on
+            # another rank's shard; only the single-process form exists here
+            raise NotImplementedError('XParity.convert_state works on unsharded vectors only in this backend')
         flip = (1 << self.L) - 1
         half = self.get_dimension()
         src = state.to_numpy()

@@ -150,6 +150,9 @@ void *dnm_vec_device_ptr(dnm_vec_t v);
 /* host <-> device, offsets/counts in elements of the LOCAL block */
 int dnm_vec_set_host(dnm_vec_t v, int64_t offset, int64_t count, const double *values);
 int dnm_vec_get_host(dnm_vec_t v, int64_t offset, int64_t count, double *values);
+/* the same for any range of the GLOBAL vector: other ranks' blocks are read through their peer
+ * mappings (the ranks must be synchronised by the caller; every rank may call it) */
+int dnm_vec_get_host_global(dnm_vec_t v, int64_t offset, int64_t count, double *values);
 /* scattered local writes / reads (Vec.setValues / vec[idxs]) */
 int dnm_vec_set_values(dnm_vec_t v, int64_t count, const int64_t *local_idx, const double *values, int add);
 int dnm_vec_get_values(dnm_vec_t v, int64_t count, const int64_t *local_idx, double *values);

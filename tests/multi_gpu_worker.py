@@ -108,6 +108,11 @@ def main():
             H.get_mat().set_option('tile_bits', 0)
             nrm = H.infinity_norm()
             check(f'norm {name}', abs(nrm - oracle.norm_inf(omsc, osub, osub)) < 1e-12 * nrm)
+            # whole vector on every rank / on rank 0 only (read through the peer mappings)
+            got_all = y.to_numpy(to_all=True)
+            check('to_numpy(to_all)', rel_err(got_all, want) < 1e-12)
+            got0 = y.to_numpy()
+            check('to_numpy rank 0 only', (got0 is None) == (rank != 0) and (rank != 0 or rel_err(got0, want) < 1e-12))
             # global reductions
             check('dot', abs(x.dot(y) - np.vdot(xfull, want)) < 1e-12)
             check('norm2', abs(y.norm() - np.linalg.norm(want)) < 1e-12)

@@ -29,3 +29,46 @@ def test_reference_arm_other_ranks_exit_quietly():
     res = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2'],
                          capture_output=True, text=True, timeout=120, env=env)
     assert res.returncode == 0 and res.stdout.strip() == ''
+
+
+def test_both_arms_describe_the_same_workload():
+    """The driver compares the two arms' `config` blocks key by key: they come from one function."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from dynamite_b200.hamiltonians import build_hamiltonian
+
+    class Args:
+        H = 'MBL'
+        no_precompute_diagonal = False
+    cfg = bench.workload_config(Args, 31, 2, build_hamiltonian('MBL', 31))
+    assert cfg['L'] == 31 and cfg['rows'] == 1 << 31 and cfg['rows_per_gpu'] == 1 << 30
+    assert cfg['unique_masks'] == 31 and cfg['nterms'] == 121 and cfg['precompute_diagonal'] is True
+    ref = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '-L', '18',
+                          '--steps', '1', '--warmup', '1', '--cpu-seconds', '0.2'],
+                         capture_output=True, text=True, timeout=300)
+    assert sorted(json.loads(ref.stdout)['config']) == sorted(cfg)
+
+
+def test_analytic_host_input_and_parity_check():
+    """bench.py's GPU arm multiplies an analytic host vector and checks sampled row blocks of the
+    result against the oracle; here the 'result' is the oracle's own full product."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import bench
+    import oracle
+    from dynamite_b200.hamiltonians import build_hamiltonian
+    L = 21
+    n = 1 << L
+    x = np.empty(n, dtype=np.complex128)
+    bench.fill_host_x(x, 0, n)
+    assert np.array_equal(x[5:105], bench.host_x(5, 100, n))
+    assert np.array_equal(x[bench.XP + 7:bench.XP + 9], bench.host_x(bench.XP + 7, 2, n))
+    half = np.empty(n // 2, dtype=np.complex128)           # rank 1 of 2
+    bench.fill_host_x(half, n // 2, n)
+    assert np.array_equal(half, x[n // 2:])
+    H = build_hamiltonian('MBL', L)
+    omsc, osub = bench.oracle_problem(H, L)
+    y, _ = oracle.matmult_fast(omsc, osub, x, nthreads=8)
+    assert bench.parity_check(H, L, y[n // 2:], n // 2, n, rows=1 << 12) < 1e-14
+    y[n // 2 + 100] += 1e-6
+    assert bench.parity_check(H, L, y[n // 2:], n // 2, n, rows=1 << 12) > 1e-9
