@@ -1432,7 +1432,7 @@ TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false, int tune = -1)
       // pipelined (persistent, TMA ring, reduce-add epilogue) wherever the tile is a TMA box and the ring fits;
       // remote operands that are read through peer mappings keep the classic kernel
       const size_t ring = (size_t)(d.nbuf + (ps.p.accumulate == 1 ? 1 : 0)) * ((size_t)16 << ps.T) + 2048;
-      // Measured on B200 (profiles/r02_pipelined_experiment.md): with 8-16 resident warps per SM the
+      // Measured on B200 (profiles/r02_experiments.md §5): with 8-16 resident warps per SM the
       // persistent kernel cannot hide the L2 latency of the FAR loads and loses to one tile per CTA
       // (4 CTAs per SM at T=11); it stays opt-in (option pipeline = 1).
       d.pipelined = A->pipeline == 1 && jit::tma_eligible(d) &&
