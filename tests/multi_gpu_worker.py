@@ -131,6 +131,22 @@ def main():
             Hv = H.dot(v0)
             Hv.axpy(-evals[0], v0)
             check(f'eigvec residual {name}', Hv.norm() < 1e-7, f'{Hv.norm():.2e}')
+        # checkpoint: rank 0 writes the header and the metadata, every rank its own block of the
+        # PETSc binary Vec; reading back gives every rank its block again
+        if name in ('MBL', 'heisenberg'):
+            import tempfile
+            x, a, b = sharded_state(sub, xfull)
+            path = os.path.join(tempfile.gettempdir(), f'dnm_ckpt_{name}_{world}')
+            x.save(path)
+            back = State.from_file(path)
+            check(f'save/from_file {name}', np.array_equal(back.vec[a:b], xfull[a:b]) and back.subspace == sub)
+            if rank == 0:
+                raw = np.fromfile(path + '.vec', dtype='>c16', offset=8)
+                check('file holds the whole vector', np.array_equal(raw, xfull))
+            dist.barrier()
+            if rank == 0:
+                os.remove(path + '.vec')
+                os.remove(path + '.metadata')
         if kind == 'full':
             x, a, b = sharded_state(sub, xfull)
             for keep in ([0, 1, 2], [L - 1], [1, L - 2, L - 1], list(range(L - 5, L))):
