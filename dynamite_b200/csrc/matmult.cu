@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(TPB)
 // the sorted list once per (block, mask) -- all masks in parallel -- the CTA stages that slice of the
 // list in shared memory with coalesced loads, and every row finishes its search there (typically
 // 8-11 shared-memory steps instead of 24 global ones at dim 10^7).  Bit-exact with S2I.
-constexpr int EX_ROWS = 256;
+constexpr int EX_ROWS_DEFAULT = 256;
 constexpr int EX_CAP = 4096;       // staged slice, states
 constexpr int EX_MAX_MASKS = 256;  // bracket table, masks
 
@@ -101,12 +101,17 @@ __device__ __forceinline__ i64 lower_bound_dev(const i64 *__restrict__ a, i64 lo
   return lo;
 }
 
+template <int EX_ROWS>
 __global__ void __launch_bounds__(EX_ROWS)
     k_mult_explicit(SubExplicit sub, MscDev msc, const double *__restrict__ diag, const cplx *__restrict__ x,
                     cplx *__restrict__ y, i64 M)
 {
+  // the staged slice: 64-bit states, or (whenever the varying bits fit) their low 32 bits -- half the
+  // shared-memory traffic and bank conflicts of the search, twice the capacity
   __shared__ i64 s_slice[EX_CAP];
+  unsigned int *s_slice32 = reinterpret_cast<unsigned int *>(s_slice);
   __shared__ i64 s_lo[EX_MAX_MASKS], s_hi[EX_MAX_MASKS];
+  __shared__ i64 s_self;  // first row whose ket has the block's prefix
   const int tid = threadIdx.x;
   for (i64 row0 = (i64)blockIdx.x * EX_ROWS; row0 < M; row0 += (i64)gridDim.x * EX_ROWS) {
     const i64 row = row0 + tid;
@@ -117,9 +122,15 @@ __global__ void __launch_bounds__(EX_ROWS)
     const i64 diff = s_min ^ s_max;
     const int h = diff ? 64 - __clzll(diff) : 0;  // bits [0, h) vary inside the block
     const i64 lowmask = (h >= 63) ? (i64)0x7fffffffffffffffll : (((i64)1 << h) - 1);
+    const bool narrow = h <= 32;
+    const int cap = narrow ? 2 * EX_CAP : EX_CAP;
     // bracket the image interval of every mask (2 searches per mask, all in parallel)
     __syncthreads();  // the previous block's tables are no longer in use
-    for (int k = tid; k < 2 * msc.nmasks; k += EX_ROWS) {
+    for (int k = tid; k < 2 * msc.nmasks + 1; k += EX_ROWS) {
+      if (k == 2 * msc.nmasks) {
+        s_self = lower_bound_dev(sub.rmap_states, 0, sub.n, s_min & ~lowmask);
+        continue;
+      }
       const int mi = k >> 1;
       const i64 P = (s_min ^ __ldg(&msc.masks[mi])) & ~lowmask;
       if (k & 1) {
@@ -141,28 +152,66 @@ __global__ void __launch_bounds__(EX_ROWS)
       mi = 1;
     }
     __syncthreads();
+    const i64 self = s_self;
+    i64 staged_lo = -1, staged_len = -1;  // the interval whose slice is in shared memory (block-uniform)
     for (; mi < msc.nmasks; ++mi) {
       const i64 c_lo = s_lo[mi], len = s_hi[mi] - c_lo;
-      const i64 bra = ket ^ __ldg(&msc.masks[mi]);
+      const i64 m = __ldg(&msc.masks[mi]);
+      const i64 bra = ket ^ m;
       i64 col = -1;
-      if (len > 0 && len <= EX_CAP) {
-        __syncthreads();  // everybody is done with the previous slice
-        for (i64 i = tid; i < len; i += EX_ROWS) s_slice[i] = __ldg(&sub.rmap_states[c_lo + i]);
-        __syncthreads();
-        int lo = 0, n = (int)len;
-        while (n > 0) {
-          const int half = n >> 1;
-          if (s_slice[lo + half] < bra) {
-            lo += half + 1;
-            n -= half + 1;
-          } else {
-            n = half;
+      bool need_search = len > 0;
+      if (len > 0 && (m & lowmask) == 0) {
+        // the mask only flips bits ABOVE the varying ones: the images keep the order of the kets.  When
+        // the image interval has the same shape as the block's own (every structured space: the low-bit
+        // patterns allowed next to the new prefix are the ones allowed next to the old) the column is the
+        // same offset into it -- one coalesced probe verifies that; any mismatch falls back to the search
+        const i64 g = c_lo + (row - self);
+        const bool hit = ok && g < c_lo + len && __ldg(&sub.rmap_states[g]) == bra;
+        if (hit) col = g;
+        need_search = __syncthreads_or(ok && !hit) != 0;
+      }
+      if (need_search) {  // (block-uniform: every thread takes part in the staging barriers)
+        if (len <= cap) {
+          // every mask that only flips varying bits maps the block into its OWN interval: that slice is
+          // staged once and reused
+          if (c_lo != staged_lo || len != staged_len) {
+            __syncthreads();  // everybody is done with the previous slice
+            if (narrow) {
+              for (i64 i = tid; i < len; i += EX_ROWS)
+                s_slice32[i] = (unsigned int)(__ldg(&sub.rmap_states[c_lo + i]) & lowmask);
+            } else {
+              for (i64 i = tid; i < len; i += EX_ROWS) s_slice[i] = __ldg(&sub.rmap_states[c_lo + i]);
+            }
+            __syncthreads();
+            staged_lo = c_lo;
+            staged_len = len;
           }
+          // branch-free lower bound: the same number of steps in every thread
+          int n = (int)len, lo = 0;
+          if (col >= 0) {
+            // already placed by the probe
+          } else if (narrow) {
+            const unsigned int key = (unsigned int)(bra & lowmask);
+            while (n > 1) {
+              const int half = n >> 1;
+              lo = (s_slice32[lo + half - 1] < key) ? lo + half : lo;
+              n -= half;
+            }
+            lo += (s_slice32[lo] < key) ? 1 : 0;
+            if (lo < (int)len && s_slice32[lo] == key) col = c_lo + lo;
+          } else {
+            while (n > 1) {
+              const int half = n >> 1;
+              lo = (s_slice[lo + half - 1] < bra) ? lo + half : lo;
+              n -= half;
+            }
+            lo += (s_slice[lo] < bra) ? 1 : 0;
+            if (lo < (int)len && s_slice[lo] == bra) col = c_lo + lo;
+          }
+        } else if (col < 0) {
+          const i64 pos = lower_bound_dev(sub.rmap_states, c_lo, len, bra);
+          if (pos < c_lo + len && __ldg(&sub.rmap_states[pos]) == bra) col = pos;
         }
-        if (lo < (int)len && s_slice[lo] == bra) col = c_lo + lo;
-      } else if (len > 0) {
-        const i64 pos = lower_bound_dev(sub.rmap_states, c_lo, len, bra);
-        if (pos < c_lo + len && __ldg(&sub.rmap_states[pos]) == bra) col = pos;
       }
       if (!ok || col < 0) continue;  // outside the subspace
       double cr, ci;
@@ -430,9 +479,13 @@ void general_mult(dnm_mat_s *A, const cplx *x, cplx *y)
   }
   if (l.type == DNM_EXPLICIT && r.type == DNM_EXPLICIT && A->same_explicit && A->left.rmap_idx.empty() &&
       A->msc.nmasks <= EX_MAX_MASKS && getenv("DNM_NO_EXPLICIT_KERNEL") == nullptr) {
-    const i64 blocks = (M + EX_ROWS - 1) / EX_ROWS;
-    const int grid = (int)std::max<i64>(1, std::min<i64>(blocks, (i64)G.sm_count * 8));
-    k_mult_explicit<<<grid, EX_ROWS, 0, G.stream>>>(A->right.explicit_dev(), A->msc, A->d_diag, x, y, M);
+    int rows = EX_ROWS_DEFAULT;
+    if (const char *e = getenv("DNM_EX_ROWS")) rows = atoi(e);
+    const i64 blocks = (M + rows - 1) / rows;
+    const int grid = (int)std::max<i64>(1, std::min<i64>(blocks, (i64)G.sm_count * 16));
+    if (rows == 128) k_mult_explicit<128><<<grid, 128, 0, G.stream>>>(A->right.explicit_dev(), A->msc, A->d_diag, x, y, M);
+    else if (rows == 512) k_mult_explicit<512><<<grid, 512, 0, G.stream>>>(A->right.explicit_dev(), A->msc, A->d_diag, x, y, M);
+    else k_mult_explicit<256><<<grid, 256, 0, G.stream>>>(A->right.explicit_dev(), A->msc, A->d_diag, x, y, M);
     count_launch();
     DNM_CHECK_CUDA(cudaGetLastError());
     return;
