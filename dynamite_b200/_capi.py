@@ -84,6 +84,8 @@ _SIGNATURES = {
     'dnm_vec_set_random': (C.c_int, [_vec, C.c_uint64]),
     'dnm_vec_copy': (C.c_int, [_vec, _vec]),
     'dnm_vec_scale': (C.c_int, [_vec, C.c_double, C.c_double]),
+    'dnm_vec_shift': (C.c_int, [_vec, C.c_double, C.c_double]),
+    'dnm_vec_normalize': (C.c_int, [_vec, C.POINTER(C.c_double)]),
     'dnm_vec_axpby': (C.c_int, [_vec, C.c_double, C.c_double, C.c_double, C.c_double, _vec]),
     'dnm_vec_dot': (C.c_int, [_vec, _vec, f64p]),
     'dnm_vec_norm': (C.c_int, [_vec, C.c_int, f64p]),
@@ -101,6 +103,8 @@ _SIGNATURES = {
                                       C.POINTER(C.c_int)]),
     'dnm_evolve': (C.c_int, [_mat, _vec, _vec, C.c_double, C.c_double, C.c_double, C.c_int,
                              C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'dnm_evolve_algo': (C.c_int, [_mat, _vec, _vec, C.c_double, C.c_double, C.c_double, C.c_int,
+                                  C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'dnm_eigsolve': (C.c_int, [_mat, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint64,
                                C.c_int, C.POINTER(C.c_int), f64p, f64p, C.POINTER(_vec),
                                C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -734,6 +734,49 @@ extern "C" int dnm_vec_scale(dnm_vec_t v, double re, double im)
   DNM_API_END
 }
 
+namespace {
+__global__ void k_shift(cplx *__restrict__ v, int64_t n, cplx a)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    cplx t = v[i];
+    t.x += a.x;
+    t.y += a.y;
+    v[i] = t;
+  }
+}
+__global__ void k_sqrt_scalar(double *v) { *v = sqrt(*v); }
+}  // namespace
+
+// Vec.shift: v[i] += a for every entry (states.py:805)
+extern "C" int dnm_vec_shift(dnm_vec_t v, double re, double im)
+{
+  DNM_API_BEGIN
+  require_init();
+  DNM_REQUIRE(v, DNM_ERR_ARG, "null vector");
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((v->local_n + 255) / 256, (int64_t)G.sm_count * 8));
+  k_shift<<<grid, 256, 0, G.stream>>>(v->d, v->local_n, make_double2(re, im));
+  count_launch();
+  DNM_CHECK_CUDA(cudaGetLastError());
+  DNM_API_END
+}
+
+// Vec.normalize: v /= ||v||_2 with the norm kept on the device between the reduction and the scaling;
+// returns the norm (a zero vector stays zero)
+extern "C" int dnm_vec_normalize(dnm_vec_t v, double *norm_out)
+{
+  DNM_API_BEGIN
+  require_init();
+  DNM_REQUIRE(v, DNM_ERR_ARG, "null vector");
+  vec_sqnorm_dev(v->d, v->local_n, G.d_scratch);
+  k_sqrt_scalar<<<1, 1, 0, G.stream>>>(G.d_scratch);
+  count_launch();
+  vec_scale_dev(v->d, v->local_n, G.d_scratch, true);
+  double nrm = 0;
+  fetch_doubles(G.d_scratch, &nrm, 1);
+  if (norm_out) *norm_out = nrm;
+  DNM_API_END
+}
+
 extern "C" int dnm_vec_axpby(dnm_vec_t y, double a_re, double a_im, double b_re, double b_im, dnm_vec_t x)
 {
   DNM_API_BEGIN

@@ -277,6 +277,9 @@ double round2(double t)
 using namespace dnm;
 typedef std::complex<double> cd;
 
+// orthogonalisation requested through dnm_evolve_algo for the next dnm_evolve: -1 = default
+static int g_evolve_algo = -1;
+
 extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re, double scale_im, double tol, int ncv,
                           int max_it, int *reason_out, int *its_out, int *matmults_out)
 {
@@ -368,7 +371,7 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
   // Hermitian operator: Lanczos recurrence (DNM_EVOLVE_ORTH=full keeps the Arnoldi column with full
   // classical Gram-Schmidt + DGKS refinement)
   const char *orth_env = getenv("DNM_EVOLVE_ORTH");
-  const bool lanczos = !(orth_env && !strcmp(orth_env, "full"));
+  const bool lanczos = g_evolve_algo >= 0 ? g_evolve_algo == 0 : !(orth_env && !strcmp(orth_env, "full"));
   // CUDA-graph capture of the basis construction: opt-in (DNM_EVOLVE_GRAPH=1).  Measured on C1 (L=20,
   // scripts/explore_c1.py): once pool_release stopped calling cudaMemGetInfo per vector the plain launch
   // sequence takes 4.7 ms per evolve, while capturing + instantiating a graph per call costs 5-70 ms.
@@ -533,6 +536,19 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
   if (its_out) *its_out = its;
   if (matmults_out) *matmults_out = matmults;
   DNM_API_END
+}
+
+extern "C" int dnm_evolve_algo(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re, double scale_im, double tol, int ncv,
+                               int max_it, int algo, int *reason_out, int *its_out, int *matmults_out)
+{
+  if (algo != 0 && algo != 1) {
+    set_error("algo must be 0 (Lanczos recurrence) or 1 (Arnoldi with full orthogonalisation)");
+    return DNM_ERR_ARG;
+  }
+  g_evolve_algo = algo;
+  const int rc = dnm_evolve(A, x, y, scale_re, scale_im, tol, ncv, max_it, reason_out, its_out, matmults_out);
+  g_evolve_algo = -1;
+  return rc;
 }
 
 extern "C" int dnm_eigsolve(dnm_mat_t A, int nev, int which, double tol, int max_it, int ncv, uint64_t seed,

@@ -210,11 +210,15 @@ class Vec:
         check(_capi.lib().dnm_vec_norm(self.handle, int(norm_type), C.byref(out)))
         return out.value
 
+    def shift(self, alpha):
+        """self[i] += alpha for every entry (petsc4py Vec.shift)"""
+        alpha = complex(alpha)
+        check(_capi.lib().dnm_vec_shift(self.handle, alpha.real, alpha.imag))
+
     def normalize(self):
-        nrm = self.norm()
-        if nrm != 0:
-            self.scale(1.0 / nrm)
-        return nrm
+        nrm = C.c_double()
+        check(_capi.lib().dnm_vec_normalize(self.handle, C.byref(nrm)))
+        return nrm.value
 
     def equal(self, other):
         if self.getSize() != other.getSize():

@@ -55,7 +55,6 @@ class MFN:
     def setType(self, t):
         if t not in ('expokit', 'krylov'):
             raise ValueError(f'unknown MFN type {t}')
-        # both requests are served by the expokit-style restarted Arnoldi scheme
         self.type = t
 
     def setDimensions(self, ncv):
@@ -76,9 +75,11 @@ class MFN:
     def solve(self, b, x):
         reason, its, mm = C.c_int(), C.c_int(), C.c_int()
         a = self.fn.alpha
-        check(_capi.lib().dnm_evolve(self.mat.handle, b.handle, x.handle, a.real, a.imag,
-                                     self.tol, self.ncv, self.max_it,
-                                     C.byref(reason), C.byref(its), C.byref(mm)))
+        # 'expokit' = sub-stepped scheme with the Lanczos recurrence, 'krylov' = the same with full
+        # Arnoldi orthogonalisation
+        check(_capi.lib().dnm_evolve_algo(self.mat.handle, b.handle, x.handle, a.real, a.imag,
+                                          self.tol, self.ncv, self.max_it, 1 if self.type == 'krylov' else 0,
+                                          C.byref(reason), C.byref(its), C.byref(mm)))
         self.reason, self.its, self.matmults = reason.value, its.value, mm.value
 
     def getConvergedReason(self):

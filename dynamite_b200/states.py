@@ -299,7 +299,11 @@ class State:
         return self
 
     def __iadd__(self, x):
-        self.axpy(1, x)
+        if isinstance(x, State):
+            self.axpy(1, x)
+        else:           # a number: added to every amplitude (reference states.py:799-807)
+            self.assert_initialized()
+            self.vec.shift(x)
         return self
 
     def __add__(self, x):

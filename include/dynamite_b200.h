@@ -162,6 +162,8 @@ int dnm_vec_set(dnm_vec_t v, double re, double im);                 /* Vec.set *
 int dnm_vec_set_random(dnm_vec_t v, uint64_t seed);
 int dnm_vec_copy(dnm_vec_t src, dnm_vec_t dst);                     /* Vec.copy */
 int dnm_vec_scale(dnm_vec_t v, double re, double im);               /* Vec.scale */
+int dnm_vec_shift(dnm_vec_t v, double re, double im);               /* Vec.shift: v[i] += a (states.py:805) */
+int dnm_vec_normalize(dnm_vec_t v, double *norm_out);               /* Vec.normalize, returns the norm */
 /* y = a*x + b*y                                                       Vec.axpby */
 int dnm_vec_axpby(dnm_vec_t y, double a_re, double a_im, double b_re, double b_im, dnm_vec_t x);
 /* out = sum_i x_i * conj(y_i)   (PETSc VecDot(x, y))                  Vec.dot */
@@ -239,6 +241,11 @@ enum {
  * capped by free device memory.  Outputs may be NULL. */
 int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re, double scale_im,
                double tol, int ncv, int max_it, int *reason, int *its, int *matmults);
+/* The same with the MFN flavour spelled out: algo 0 = expokit sub-stepping with the Lanczos recurrence
+ * (default: the operator is Hermitian), 1 = expokit sub-stepping with full Arnoldi orthogonalisation
+ * (MFN type "krylov" is served by it). */
+int dnm_evolve_algo(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re, double scale_im,
+                    double tol, int ncv, int max_it, int algo, int *reason, int *its, int *matmults);
 
 /* Hermitian eigensolve by thick-restart Lanczos (Krylov-Schur), i.e. what
  * computations.eigsolve gets from SLEPc.EPS HEP with the default solver

@@ -370,3 +370,31 @@ def test_compute_rcm_device(gpu, name, L, start):
         rc_h, _, _ = run(lib.dnm_compute_rcm, dim_h - 3)
         rc_d, _, _ = run(lib.dnm_compute_rcm_device, dim_h - 3)
         assert rc_h != 0 and rc_d != 0          # 'state_map size too small' from both
+
+
+def test_vec_shift_normalize_and_evolve_algo(gpu):
+    """C-ABI entries that complete the reference's Vec / MFN surface: Vec.shift (states.py:805),
+    Vec.normalize on the device, and the MFN type passed to dnm_evolve_algo."""
+    import scipy.linalg
+    from dynamite_b200 import msc_tools
+    from dynamite_b200.hamiltonians import build_hamiltonian
+    from dynamite_b200.states import State
+    from dynamite_b200.subspaces import Full
+    L = 8
+    s = State(L=L, state='random', seed=5)
+    v = s.to_numpy().copy()
+    s += 0.25 - 0.5j                       # a number: added to every amplitude
+    assert np.allclose(s.to_numpy(), v + (0.25 - 0.5j), atol=1e-15)
+    nrm = s.vec.normalize()
+    assert abs(nrm - np.linalg.norm(v + (0.25 - 0.5j))) < 1e-13 and abs(s.norm() - 1) < 1e-14
+    H = build_hamiltonian('MBL', L)
+    H.subspace = Full(L=L)
+    H.reduce_msc()
+    full = oracle.Subspace({'type': 'full', 'L': L})
+    A = msc_tools.msc_to_numpy(H.msc, (256, 256), full.i2s, full.s2i)
+    A = np.asarray(A.todense() if hasattr(A, 'todense') else A, dtype=np.complex128)
+    psi = State(L=L, state='random', seed=6)
+    want = scipy.linalg.expm(-1.3j * A) @ psi.to_numpy()
+    for algo in ('expokit', 'krylov'):
+        got = H.evolve(psi, 1.3, tol=1e-12, algo=algo).to_numpy()
+        assert np.linalg.norm(got - want) < 1e-10, algo
