@@ -67,6 +67,9 @@ _SIGNATURES = {
     'dnm_subspace_i2s': (C.c_int, [_sp, C.c_int64, i64p, i64p]),
     'dnm_compute_rcm': (C.c_int, [C.c_int64, i64p, i64p, f64p, i64p, C.c_int64, C.c_int64,
                                   C.c_int64, i64p]),
+    'dnm_jit_dryrun': (C.c_int, [C.c_int64, i64p, i64p, i64p, f64p, _sp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_char_p, C.c_int64, i64p, i64p, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'dnm_compute_rcm_device': (C.c_int, [C.c_int64, i64p, i64p, f64p, i64p, C.c_int64, C.c_int64,
                                   C.c_int64, i64p]),
     'dnm_subspace_s2i_device': (C.c_int, [_sp, C.c_int64, i64p, i64p]),

@@ -21,6 +21,7 @@
 #include "matmult_tiled.h"
 
 #include <algorithm>
+#include <cstring>
 #include <map>
 #include <string>
 #include <memory>
@@ -262,9 +263,19 @@ int ilog2(i64 v)
   return n;
 }
 
+// dnm_jit_dryrun: plan and generate on the host only (no device allocations, no module load), so that
+// the generator can be exercised -- and its output compiled by NVRTC -- on a machine without a GPU
+bool g_plan_host_only = false;
+struct DryRun {
+  std::string src, log;
+  size_t cubin_bytes = 0;
+  int kernels = 0, remote_groups = 0, passes = 0, pipelined = 0;
+} g_dry;
+
 template <class Tv>
 Tv *up(const std::vector<Tv> &h, std::vector<void *> &owned)
 {
+  if (g_plan_host_only) return nullptr;
   Tv *d = nullptr;
   const size_t bytes = sizeof(Tv) * std::max<size_t>(h.size(), 1);
   DNM_CHECK_CUDA(cudaMalloc(&d, bytes));
@@ -1383,7 +1394,7 @@ TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false, int tune = -1)
   bool has_far = false;
   if (best)
     for (const Pass &ps : best->passes) has_far = has_far || ps.nfar > 0;
-  if (best && !has_far && A->jit != 1 && batchable(*best)) {
+  if (best && !has_far && A->jit != 1 && !g_plan_host_only && batchable(*best)) {
     const Pass &p0 = best->passes[0];
     {
       std::vector<PassParams> all;
@@ -1451,6 +1462,17 @@ TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false, int tune = -1)
           fclose(f);
         }
       }
+      if (g_plan_host_only) {
+        g_dry.src = src;
+        g_dry.cubin_bytes = jit::compile_cubin(src, log).size();
+        g_dry.log = log;
+        g_dry.kernels = (int)descs.size();
+        g_dry.passes = (int)best->passes.size();
+        g_dry.remote_groups = g_dry.pipelined = 0;
+        for (const Pass &ps : best->passes) g_dry.remote_groups += ps.nremote;
+        for (const jit::PassDesc &d : descs) g_dry.pipelined += d.pipelined ? 1 : 0;
+        return best.release();
+      }
       best->jit = jit::compile(src, descs, log);
       if (!best->jit && best->fold && !no_fold) {
         // folded remote masks only exist in generated code: plan again the classic way
@@ -1472,7 +1494,7 @@ TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false, int tune = -1)
       }
     }
   }
-  DNM_CHECK_CUDA(cudaStreamSynchronize(G.stream));
+  if (!g_plan_host_only) DNM_CHECK_CUDA(cudaStreamSynchronize(G.stream));
   return best.release();
 }
 
@@ -1790,3 +1812,71 @@ void tiled_norm(dnm_mat_s *A, double *d_out)
 }
 
 }  // namespace dnm
+
+// Host-only dry run of the planner + generator + NVRTC (no GPU needed): plans the MatMult of a
+// Full/Parity operator as rank `rank` of `nranks` would, generates the pass kernels and compiles them
+// to a cubin for sm_100a.  tune_shape: -1 = the default heuristics, >= 0 = one autotuner shape.
+extern "C" int dnm_jit_dryrun(int64_t nmasks, const int64_t *masks, const int64_t *mask_offsets, const int64_t *signs,
+                              const double *coeffs, const dnm_subspace_t *sub, int nranks, int rank, int tile_bits,
+                              int far_bits, int pipeline, int tune_shape, char *src_out, int64_t src_cap, int64_t *src_len,
+                              int64_t *cubin_bytes, int *n_kernels, int *n_passes, int *n_remote_groups, int *n_pipelined)
+{
+  DNM_API_BEGIN
+  using namespace dnm;
+  DNM_REQUIRE(nmasks >= 1 && masks && mask_offsets && signs && coeffs && sub, DNM_ERR_ARG, "null or empty arguments");
+  DNM_REQUIRE(nranks >= 1 && nranks <= MAX_RANKS && (nranks & (nranks - 1)) == 0 && rank >= 0 && rank < nranks, DNM_ERR_ARG,
+              "bad rank layout");
+  DNM_REQUIRE(tune_shape < N_TUNE_SHAPES, DNM_ERR_ARG, "tune_shape out of range");
+  const int64_t nterms = mask_offsets[nmasks];
+  dnm_mat_s A;
+  A.masks.assign(masks, masks + nmasks);
+  A.mask_offsets.assign(mask_offsets, mask_offsets + nmasks + 1);
+  A.signs.assign(signs, signs + nterms);
+  A.coeffs.assign(coeffs, coeffs + 2 * nterms);
+  A.left.copy_from(sub);
+  A.right.copy_from(sub);
+  A.M = A.N = A.left.dim;
+  DNM_REQUIRE(tiled_supported(&A), DNM_ERR_UNSUPPORTED, "the tiled MatMult needs a Full or Parity subspace");
+  A.local_M = A.local_N = A.M / nranks;
+  // a cached diagonal is assumed (as benchmark.py builds its matrices): only its presence matters to the planner
+  A.d_diag = A.masks[0] == 0 ? reinterpret_cast<double *>(0x10) : nullptr;
+  A.jit = 1;
+  A.tile_bits = tile_bits;
+  A.far_bits = far_bits;
+  A.pipeline = pipeline;
+  const int save_n = G.nranks, save_r = G.rank;
+  G.nranks = nranks;
+  G.rank = rank;
+  g_plan_host_only = true;
+  g_dry = DryRun();
+  TiledPlan *plan = nullptr;
+  try {
+    plan = build_plan(&A, false, tune_shape);
+  } catch (...) {
+    g_plan_host_only = false;
+    G.nranks = save_n;
+    G.rank = save_r;
+    A.d_diag = nullptr;
+    throw;
+  }
+  g_plan_host_only = false;
+  G.nranks = save_n;
+  G.rank = save_r;
+  A.d_diag = nullptr;
+  delete plan;
+  if (src_len) *src_len = (int64_t)g_dry.src.size();
+  if (src_out && src_cap > 0) {
+    const size_t n = std::min<size_t>((size_t)src_cap - 1, g_dry.src.size());
+    memcpy(src_out, g_dry.src.data(), n);
+    src_out[n] = 0;
+  }
+  if (cubin_bytes) *cubin_bytes = (int64_t)g_dry.cubin_bytes;
+  if (n_kernels) *n_kernels = g_dry.kernels;
+  if (n_passes) *n_passes = g_dry.passes;
+  if (n_remote_groups) *n_remote_groups = g_dry.remote_groups;
+  if (n_pipelined) *n_pipelined = g_dry.pipelined;
+  DNM_REQUIRE(g_dry.kernels == 0 || g_dry.cubin_bytes > 0, DNM_ERR_INTERNAL, "NVRTC rejected the generated source: %s",
+              g_dry.log.c_str());
+  DNM_API_END
+}
+

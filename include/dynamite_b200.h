@@ -217,6 +217,15 @@ int dnm_mat_set_option(dnm_mat_t A, const char *key, int64_t value);
 /* keys: "kernel", "passes", "jit_passes" (passes running generated kernels), "tuned_shape",
  * "unique_masks", "nterms", "model_bytes", "compulsory_bytes", "launches_per_mult", "has_diag" */
 int dnm_mat_get_info(dnm_mat_t A, const char *key, double *value);
+/* Diagnostics, no GPU needed: plan the tiled MatMult of a Full/Parity operator as rank `rank` of
+ * `nranks` would, generate the operator-specialised pass kernels (csrc/jit.cu) and compile them with
+ * NVRTC to an sm_100a cubin.  tune_shape -1 = default heuristics, >= 0 = one autotuner shape.  The
+ * generated source is copied to src_out (src_cap bytes, NUL-terminated) when given. */
+int dnm_jit_dryrun(int64_t nmasks, const int64_t *masks, const int64_t *mask_offsets,
+                   const int64_t *signs, const double *coeffs, const dnm_subspace_t *sub, int nranks,
+                   int rank, int tile_bits, int far_bits, int pipeline, int tune_shape, char *src_out,
+                   int64_t src_cap, int64_t *src_len, int64_t *cubin_bytes, int *n_kernels,
+                   int *n_passes, int *n_remote_groups, int *n_pipelined);
 /* CheckConserves  _backend/bpetsc_template_2.c:990-1056 (bpetsc.pyx:150-193) */
 int dnm_check_conserves(int64_t nmasks, const int64_t *masks, const int64_t *mask_offsets,
                         const int64_t *signs, const double *coeffs,
