@@ -70,6 +70,7 @@ _SIGNATURES = {
     'dnm_jit_dryrun': (C.c_int, [C.c_int64, i64p, i64p, i64p, f64p, _sp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_char_p, C.c_int64, i64p, i64p, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                  C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'dnm_jit_set_host_emulation': (C.c_int, [C.c_int]),
     'dnm_compute_rcm_device': (C.c_int, [C.c_int64, i64p, i64p, f64p, i64p, C.c_int64, C.c_int64,
                                   C.c_int64, i64p]),
     'dnm_subspace_s2i_device': (C.c_int, [_sp, C.c_int64, i64p, i64p]),

@@ -535,6 +535,28 @@ int pipelined_ctas(const PassDesc &pd)
   return std::max(1, std::min(std::min(by_smem, by_threads), 4));
 }
 
+// Host emulation (tests only, dnm_jit_set_host_emulation): the SAME kernel bodies are emitted, but the
+// prelude defines the CUDA vocabulary for a C++ compiler (one OS thread per CUDA thread, a pthread
+// barrier for __syncthreads) and the TMA helpers become plain box copies / box additions.  The CUDA
+// output is not touched by this mode.
+bool g_host_emulation = false;
+
+// nested loops over the box of `bx` (innermost dimension fastest): the statement sees `gi` = element
+// offset in the global tensor (doubles) and `si` = running offset in shared memory (doubles)
+void emit_host_box_loops(Out &o, const Box &bx, const char *stmt)
+{
+  o("  long long si = 0;\n");
+  for (int d = bx.rank - 1; d >= 0; --d)
+    o("  %*sfor (long long i%d = 0; i%d < %u; ++i%d)\n", 2 * (bx.rank - 1 - d), "", d, d, bx.box[d], d);
+  std::string gi = "0";
+  for (int d = 0; d < bx.rank; ++d) {
+    char buf[96];
+    snprintf(buf, sizeof(buf), " + (c[%d] + i%d) * %lldll", d, d, (long long)(d == 0 ? 1 : bx.strides[d] / 8));
+    gi += buf;
+  }
+  o("  %*s{ const long long gi = %s; %s ++si; }\n", 2 * bx.rank, "", gi.c_str(), stmt);
+}
+
 // outer_p<k>(tile) = index bits outside the window; load_p<k> = TMA load of a tile into shared memory
 // (signals `bar`); reduce_p<k> = cp.reduce.async.bulk.tensor add of a result tile into y
 void emit_tma_helpers(Out &o, const PassDesc &pd, int index, const Box &bx, bool reduce)
@@ -557,7 +579,16 @@ void emit_tma_helpers(Out &o, const PassDesc &pd, int index, const Box &bx, bool
   o("__device__ __forceinline__ void load_p%d(const TMap *tmx, const double2 *x, u64 tb, void *dst, u64 *bar)\n{\n", index);
   o("  const i64 outer = outer_p%d(tb);\n", index);
   o("  mbar_expect_tx(bar, %uu);\n", tile_bytes);
-  if (bx.rank == 0) {
+  if (g_host_emulation) {
+    if (bx.rank == 0) {
+      o("  memcpy(dst, x + outer, %uu);\n", tile_bytes);
+    } else {
+      o("  const int c[%d] = {%s};\n", bx.rank, coords().c_str());
+      o("  const double *g = tmx->base;\n  double *sm = (double *)dst;\n");
+      emit_host_box_loops(o, bx, "sm[si] = g[gi];");
+    }
+    o("  emu_bar_complete(bar);\n}\n");
+  } else if (bx.rank == 0) {
     o("  asm volatile(\"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%%0], [%%1], %%2, [%%3];\" "
       "::\"r\"(smem_u32(dst)), \"l\"(x + outer), \"r\"(%uu), \"r\"(smem_u32(bar)) : \"memory\");\n",
       tile_bytes);
@@ -575,8 +606,15 @@ void emit_tma_helpers(Out &o, const PassDesc &pd, int index, const Box &bx, bool
       "::\"r\"(smem_u32(dst)), \"l\"(tmx), \"r\"(smem_u32(bar))%s : \"memory\");\n",
       bx.rank, ops.c_str(), cl.c_str());
   }
-  o("}\n");
-  if (reduce) {
+  if (!g_host_emulation) o("}\n");
+  if (reduce && g_host_emulation) {
+    o("__device__ __forceinline__ void reduce_p%d(const TMap *tmy, u64 tb, const void *src)\n{\n", index);
+    o("  const i64 outer = outer_p%d(tb);\n", index);
+    o("  const int c[%d] = {%s};\n", bx.rank, coords().c_str());
+    o("  double *g = const_cast<double *>(tmy->base);\n  const double *sm = (const double *)src;\n");
+    emit_host_box_loops(o, bx, "g[gi] += sm[si];");
+    o("}\n");
+  } else if (reduce) {
     o("__device__ __forceinline__ void reduce_p%d(const TMap *tmy, u64 tb, const void *src)\n{\n", index);
     o("  const i64 outer = outer_p%d(tb);\n", index);
     std::string ops, cl;
@@ -770,13 +808,118 @@ const char *PRELUDE =
 
 bool tma_eligible(const PassDesc &pd) { return tile_box(pd).rank >= 0; }
 
+void set_host_emulation(bool on) { g_host_emulation = on; }
+bool host_emulation() { return g_host_emulation; }
+
+namespace {
+const char *HOST_PRELUDE =
+    "// generated by dynamite_b200 (csrc/jit.cu) in HOST EMULATION mode: the kernel bodies below are the ones\n"
+    "// that run on the GPU; this prelude maps the CUDA vocabulary to C++ (tests/test_jit_emulation.py)\n"
+    "#include <cmath>\n#include <cstdlib>\n#include <cstring>\n#include <pthread.h>\n#include <sched.h>\n"
+    "typedef long long i64;\ntypedef unsigned long long u64;\ntypedef unsigned int u32;\n"
+    "struct double2 { double x, y; };\n"
+    "static inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; return v; }\n"
+    "struct TMap { const double *base; };\n"
+    "struct Peers { const double2 *p[16]; };\n"
+    "struct EmuIdx { unsigned x; };\n"
+    "static thread_local EmuIdx threadIdx, blockIdx, gridDim;\n"
+    "static unsigned char *emu_smem_base;\nstatic pthread_barrier_t emu_barrier;\n"
+    "#define __global__\n#define __device__\n#define __forceinline__ inline\n#define __launch_bounds__(a, b)\n"
+    "#define __grid_constant__\n#define __align__(n)\n"
+    "static inline void __syncthreads() { pthread_barrier_wait(&emu_barrier); }\n"
+    "static inline int __popc(u32 v) { return __builtin_popcount(v); }\n"
+    "static inline int __popcll(u64 v) { return __builtin_popcountll(v); }\n"
+    "template <class T> static inline T __ldg(const T *p) { return *p; }\n"
+    "template <class T> static inline T __ldcs(const T *p) { return *p; }\n"
+    "template <class T> static inline T __ldcg(const T *p) { return *p; }\n"
+    "static inline void __stcs(double2 *p, double2 v) { *p = v; }\n"
+    "static inline void st_plain(double2 *p, double2 v) { *p = v; }\n"
+    "static inline void cpa16(void *s, const void *g) { memcpy(s, g, 16); }\n"
+    "static inline void cpa_wait() {}\nstatic inline void cpa_commit() {}\nstatic inline void cpa_wait_all() {}\n"
+    "static inline void cpa_wait_first() {}\n"
+    "static inline void mbar_init(u64 *bar, int) { __atomic_store_n(bar, 0ull, __ATOMIC_RELEASE); }\n"
+    "static inline void mbar_expect_tx(u64 *, u32) {}\n"
+    "// an mbarrier as the count of completed phases: wait(parity) returns once the phase of that parity is over\n"
+    "static inline void emu_bar_complete(u64 *bar) { __atomic_add_fetch(bar, 1ull, __ATOMIC_RELEASE); }\n"
+    "static inline void mbar_wait(u64 *bar, u32 parity)\n{\n"
+    "  while ((__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1ull) == (u64)parity) sched_yield();\n}\n\n";
+
+void replace_all(std::string &s, const std::string &from, const std::string &to)
+{
+  for (size_t pos = 0; (pos = s.find(from, pos)) != std::string::npos; pos += to.size()) s.replace(pos, from.size(), to);
+}
+}  // namespace
+
 std::string generate(const std::vector<PassDesc> &passes)
 {
   Out o;
-  o.s = PRELUDE;
+  o.s = g_host_emulation ? HOST_PRELUDE : PRELUDE;
   for (size_t k = 0; k < passes.size(); ++k) {
     if (passes[k].pipelined) gen_pipelined(o, passes[k], (int)k);
     else gen_classic(o, passes[k], (int)k);
+  }
+  if (g_host_emulation) {
+    // the few CUDA-only statements inside the kernel bodies
+    replace_all(o.s, "asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\");", ";");
+    replace_all(o.s, "asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");", ";");
+    replace_all(o.s, "asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");", ";");
+    replace_all(o.s, "asm volatile(\"cp.async.bulk.wait_group 0;\" ::: \"memory\");", ";");
+    replace_all(o.s, "extern __shared__ __align__(1024) unsigned char smem[];", "unsigned char *smem = emu_smem_base;");
+    replace_all(o.s, "extern __shared__ double2 tile[];", "double2 *tile = reinterpret_cast<double2 *>(emu_smem_base);");
+    // a uniform entry point per pass, the table of passes and the harness that walks it: the threads of a
+    // block are OS threads, the blocks of a grid run one after the other
+    Out t;
+    for (size_t k = 0; k < passes.size(); ++k) {
+      const PassDesc &pd = passes[k];
+      const bool tma = !pd.pipelined && pd.tma_stage;
+      t("static void emu_run_p%zu(const double2 *x, double2 *y, const double *diag, i64 rank_bits, u64 ntiles, Peers xs)\n{\n", k);
+      if (pd.pipelined || tma) {
+        t("  TMap tx; tx.base = (const double *)x;\n  TMap ty; ty.base = (const double *)y;\n");
+        t("  dnm_jit_p%zu(tx, ty, x, y, diag, rank_bits, ntiles, xs);\n}\n", k);
+      } else {
+        t("  (void)ntiles;\n  dnm_jit_p%zu(x, y, diag, rank_bits, xs);\n}\n", k);
+      }
+    }
+    t("struct EmuPass {\n  void (*run)(const double2 *, double2 *, const double *, i64, u64, Peers);\n"
+      "  int threads, T, pipelined;\n  i64 rank_bits;\n  long long smem;\n};\n");
+    t("static const EmuPass emu_passes[] = {\n");
+    for (size_t k = 0; k < passes.size(); ++k) {
+      const PassDesc &pd = passes[k];
+      const Geo g(pd);
+      const int nrem = pd.stage_remote ? remote_groups(pd) : 0;
+      t("  {emu_run_p%zu, %d, %d, %d, 0x%llxll, %lldll},\n", k, g.NT, pd.T, pd.pipelined ? 1 : 0, (u64)pd.p->rank_bits,
+        (long long)(((size_t)16 << pd.T) * (size_t)(8 + nrem) + 4096));
+    }
+    t("};\n");
+    t("struct EmuJob { const EmuPass *ps; const double2 *x; double2 *y; const double *diag; u64 ntiles; unsigned grid; Peers xs; };\n"
+      "struct EmuThread { const EmuJob *job; unsigned tid; };\n"
+      "static void *emu_thread(void *arg)\n{\n"
+      "  const EmuThread *t = (const EmuThread *)arg;\n  const EmuJob *j = t->job;\n"
+      "  threadIdx.x = t->tid;\n  gridDim.x = j->grid;\n"
+      "  for (unsigned b = 0; b < j->grid; ++b) {\n    blockIdx.x = b;\n"
+      "    j->ps->run(j->x, j->y, j->diag, j->ps->rank_bits, j->ntiles, j->xs);\n"
+      "    pthread_barrier_wait(&emu_barrier);  // the next block reuses the shared memory\n  }\n  return 0;\n}\n");
+    // peers[h] = the input shard of rank (this ^ h); peers[0] = the local shard.  Pipelined grids are kept to
+    // `pipelined_grid` CTAs so that every CTA walks its ring more than once.
+    t("extern \"C\" int dnm_emu_npasses() { return %zu; }\n", passes.size());
+    t("extern \"C\" int dnm_emu_mult(const double2 *const *peers, int npeers, double2 *y, const double *diag, long long nloc_rows,\n"
+      "                            int pipelined_grid)\n{\n"
+      "  Peers xs;\n  for (int h = 0; h < 16; ++h) xs.p[h] = h < npeers ? peers[h] : 0;\n"
+      "  for (int k = 0; k < %zu; ++k) {\n    const EmuPass *ps = &emu_passes[k];\n"
+      "    EmuJob job;\n    job.ps = ps;\n    job.x = peers[0];\n    job.y = y;\n    job.diag = k == 0 ? diag : 0;\n"
+      "    job.ntiles = (u64)nloc_rows >> ps->T;\n    job.xs = xs;\n"
+      "    job.grid = (unsigned)job.ntiles;\n"
+      "    if (ps->pipelined && job.grid > (unsigned)pipelined_grid) job.grid = (unsigned)pipelined_grid;\n"
+      "    emu_smem_base = (unsigned char *)aligned_alloc(1024, (size_t)ps->smem);\n"
+      "    if (!emu_smem_base) return 1;\n"
+      "    pthread_barrier_init(&emu_barrier, 0, (unsigned)ps->threads);\n"
+      "    pthread_t *th = new pthread_t[ps->threads];\n    EmuThread *ta = new EmuThread[ps->threads];\n"
+      "    for (int i = 0; i < ps->threads; ++i) {\n      ta[i].job = &job;\n      ta[i].tid = (unsigned)i;\n"
+      "      if (pthread_create(&th[i], 0, emu_thread, &ta[i]) != 0) return 2;\n    }\n"
+      "    for (int i = 0; i < ps->threads; ++i) pthread_join(th[i], 0);\n"
+      "    delete[] th;\n    delete[] ta;\n    pthread_barrier_destroy(&emu_barrier);\n    free(emu_smem_base);\n  }\n  return 0;\n}\n",
+      passes.size());
+    o.s += t.s;
   }
   return o.s;
 }

@@ -74,6 +74,10 @@ struct PassDesc {
 // can this window be fetched as one TMA box?
 bool tma_eligible(const PassDesc &pd);
 
+// tests: emit the same kernel bodies for a C++ compiler (CUDA vocabulary emulated by the prelude)
+void set_host_emulation(bool on);
+bool host_emulation();
+
 // CUDA source of one kernel per pass, named dnm_jit_p<k>
 std::string generate(const std::vector<PassDesc> &passes);
 

@@ -270,6 +270,7 @@ struct DryRun {
   std::string src, log;
   size_t cubin_bytes = 0;
   int kernels = 0, remote_groups = 0, passes = 0, pipelined = 0;
+  bool host = false;
 } g_dry;
 
 template <class Tv>
@@ -1464,7 +1465,8 @@ TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false, int tune = -1)
       }
       if (g_plan_host_only) {
         g_dry.src = src;
-        g_dry.cubin_bytes = jit::compile_cubin(src, log).size();
+        g_dry.host = jit::host_emulation();
+        if (!g_dry.host) g_dry.cubin_bytes = jit::compile_cubin(src, log).size();  // (host source is for a C++ compiler)
         g_dry.log = log;
         g_dry.kernels = (int)descs.size();
         g_dry.passes = (int)best->passes.size();
@@ -1816,6 +1818,13 @@ void tiled_norm(dnm_mat_s *A, double *d_out)
 // Host-only dry run of the planner + generator + NVRTC (no GPU needed): plans the MatMult of a
 // Full/Parity operator as rank `rank` of `nranks` would, generates the pass kernels and compiles them
 // to a cubin for sm_100a.  tune_shape: -1 = the default heuristics, >= 0 = one autotuner shape.
+extern "C" int dnm_jit_set_host_emulation(int on)
+{
+  DNM_API_BEGIN
+  dnm::jit::set_host_emulation(on != 0);
+  DNM_API_END
+}
+
 extern "C" int dnm_jit_dryrun(int64_t nmasks, const int64_t *masks, const int64_t *mask_offsets, const int64_t *signs,
                               const double *coeffs, const dnm_subspace_t *sub, int nranks, int rank, int tile_bits,
                               int far_bits, int pipeline, int tune_shape, char *src_out, int64_t src_cap, int64_t *src_len,
@@ -1875,7 +1884,7 @@ extern "C" int dnm_jit_dryrun(int64_t nmasks, const int64_t *masks, const int64_
   if (n_passes) *n_passes = g_dry.passes;
   if (n_remote_groups) *n_remote_groups = g_dry.remote_groups;
   if (n_pipelined) *n_pipelined = g_dry.pipelined;
-  DNM_REQUIRE(g_dry.kernels == 0 || g_dry.cubin_bytes > 0, DNM_ERR_INTERNAL, "NVRTC rejected the generated source: %s",
+  DNM_REQUIRE(g_dry.kernels == 0 || g_dry.host || g_dry.cubin_bytes > 0, DNM_ERR_INTERNAL, "NVRTC rejected the generated source: %s",
               g_dry.log.c_str());
   DNM_API_END
 }

@@ -226,6 +226,12 @@ int dnm_jit_dryrun(int64_t nmasks, const int64_t *masks, const int64_t *mask_off
                    int rank, int tile_bits, int far_bits, int pipeline, int tune_shape, char *src_out,
                    int64_t src_cap, int64_t *src_len, int64_t *cubin_bytes, int *n_kernels,
                    int *n_passes, int *n_remote_groups, int *n_pipelined);
+/* Tests only: while on, dnm_jit_dryrun emits the SAME pass kernels for a C++ compiler -- a prelude
+ * maps the CUDA vocabulary to the host (one OS thread per CUDA thread, TMA boxes as copy loops) and
+ * an `extern "C" dnm_emu_mult` harness walks the passes -- and skips NVRTC (cubin_bytes = 0).  The
+ * product never sets it: tests/test_jit_emulation.py checks what the generated code computes
+ * against the oracle on machines without a GPU. */
+int dnm_jit_set_host_emulation(int on);
 /* CheckConserves  _backend/bpetsc_template_2.c:990-1056 (bpetsc.pyx:150-193) */
 int dnm_check_conserves(int64_t nmasks, const int64_t *masks, const int64_t *mask_offsets,
                         const int64_t *signs, const double *coeffs,

@@ -1,0 +1,163 @@
+"""CPU (no GPU): what the GENERATED pass kernels compute, checked against the oracle.
+
+dnm_jit_set_host_emulation(1) makes dnm_jit_dryrun emit the same kernel bodies it hands to NVRTC, with
+a prelude that maps the CUDA vocabulary to C++: every CUDA thread of a block is an OS thread,
+__syncthreads is a pthread barrier, cp.async copies are memcpy, the TMA tile load / reduce-add of a
+tensor box become the box's nested copy / add loops, an mbarrier is a phase counter.  The source is
+compiled with g++ and the passes of one MatMult are run on random vectors; the result must agree
+with oracle.matmult (the restatement of the reference's MatMult_CPU) to rounding.  The plans are small
+(2^13..2^16 rows per rank) but go through the same planner and generator as the L = 30..33 ones:
+windows, FAR masks, TMA boxes, lean coefficient forms, pipelined rings and folded remote masks (the
+peer shards are ordinary arrays here).
+
+The GPU execution of the very same source is covered by tests/test_gpu_matmult.py and
+tests/multi_gpu_worker.py; this file is what guards the generator where no GPU is present."""
+import ctypes as C
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from dynamite_b200 import _capi, msc_tools
+from dynamite_b200.hamiltonians import build_hamiltonian
+from dynamite_b200.subspaces import Full, Parity
+
+from test_jit_generator import dryrun
+
+
+class Emulated:
+    """One rank's generated passes, compiled for the host."""
+
+    def __init__(self, tmp_path, name, L, tag, **kw):
+        lib = _capi.lib()
+        assert lib.dnm_jit_set_host_emulation(1) == 0
+        try:
+            self.info = dryrun(name, L, **kw)
+        finally:
+            lib.dnm_jit_set_host_emulation(0)
+        assert self.info['cubin'] == 0                       # NVRTC is not involved in this mode
+        assert self.info['kernels'] == self.info['passes'] >= 1, self.info
+        src = tmp_path / f'emu_{tag}.cpp'
+        so = tmp_path / f'emu_{tag}.so'
+        src.write_text(self.info['src'])
+        res = subprocess.run(['g++', '-O1', '-shared', '-fPIC', '-pthread', '-o', str(so), str(src)],
+                             capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stderr[-3000:]
+        self.lib = C.CDLL(str(so))
+        self.lib.dnm_emu_mult.restype = C.c_int
+        self.lib.dnm_emu_mult.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]
+        assert self.lib.dnm_emu_npasses() == self.info['passes']
+
+    def mult(self, shards, diag, pipelined_grid=3):
+        """shards[h] = the input shard of rank (this ^ h); returns this rank's rows of the product."""
+        n = shards[0].size
+        y = np.full(n, np.nan + 1j * np.nan, dtype=np.complex128)      # pass 0 must write every row
+        ptrs = (C.c_void_p * len(shards))(*[s.ctypes.data for s in shards])
+        rc = self.lib.dnm_emu_mult(ptrs, len(shards), y.ctypes.data, diag.ctypes.data if diag is not None else None,
+                                   n, pipelined_grid)
+        assert rc == 0
+        return y
+
+
+def oracle_subspace(sub, L):
+    if isinstance(sub, Parity):
+        return oracle.Subspace({'type': 'parity', 'L': L, 'space': sub.space})
+    return oracle.Subspace({'type': 'full', 'L': L})
+
+
+def reference_product(name, L, sub, x):
+    """(y, diag): the oracle's product and the cached diagonal the planner assumes (mask-0 terms)."""
+    H = build_hamiltonian(name, L)
+    H.reduce_msc()
+    masks, offs = msc_tools.mask_offsets(H.msc)
+    osub = oracle_subspace(sub, L)
+    omsc = oracle.Msc(masks, offs, H.msc['signs'], H.msc['coeffs'])
+    y = oracle.matmult(omsc, osub, osub, x)
+    diag = None
+    if masks[0] == 0:
+        n0 = int(offs[1])
+        dmsc = oracle.Msc(masks[:1], offs[:2], H.msc['signs'][:n0], H.msc['coeffs'][:n0])
+        d = oracle.matmult(dmsc, osub, osub, np.ones(x.size, dtype=np.complex128))
+        assert np.all(d.imag == 0)
+        diag = np.ascontiguousarray(d.real)
+    return y, diag
+
+
+def random_state(n, seed):
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal(n) + 1j * rng.standard_normal(n)
+
+
+def check(tmp_path, name, L, sub=None, nranks=1, seed=0, **kw):
+    sub = sub if sub is not None else Full(L=L)
+    dim = sub.get_dimension()
+    x = random_state(dim, seed)
+    y_ref, diag = reference_product(name, L, sub, x)
+    nloc = dim // nranks
+    scale = np.abs(y_ref).max()
+    infos = []
+    for rank in range(nranks):
+        emu = Emulated(tmp_path, name, L, f'{name}_{L}_{nranks}_{rank}', sub=sub, nranks=nranks, rank=rank, **kw)
+        shards = [np.ascontiguousarray(x[(rank ^ h) * nloc:((rank ^ h) + 1) * nloc]) for h in range(nranks)]
+        d = None if diag is None else np.ascontiguousarray(diag[rank * nloc:(rank + 1) * nloc])
+        y = emu.mult(shards, d)
+        err = np.abs(y - y_ref[rank * nloc:(rank + 1) * nloc]).max() / scale
+        assert err < 1e-14, (name, L, rank, err)       # f64 sums in a different order: rounding only
+        infos.append(emu.info)
+    return infos
+
+
+@pytest.mark.parametrize('name', ['MBL', 'heisenberg', 'long_range', 'ising', 'XX'])
+def test_generated_passes_match_oracle(tmp_path, name):
+    infos = check(tmp_path, name, 14, tile_bits=9, far_bits=2)
+    assert infos[0]['passes'] >= 2
+
+
+def test_far_masks_and_tma_boxes(tmp_path):
+    """The default L=30 shape in miniature: a writing pass on the contiguous tile and an accumulating
+    pass whose window is a tensor box, the masks that leave the window served as FAR loads."""
+    info = check(tmp_path, 'MBL', 15, tile_bits=9, far_bits=3)[0]
+    assert ' FAR' in info['src'] and 'reduce_p' in info['src'] and 'load_p' in info['src']
+    info = check(tmp_path, 'MBL', 15, tile_bits=10, far_bits=0)[0]
+    assert ' FAR' not in info['src']
+
+
+def test_cp_async_staging_and_plain_accumulate(tmp_path, monkeypatch):
+    monkeypatch.setenv('DNM_JIT_TMA', '0')
+    info = check(tmp_path, 'heisenberg', 14, tile_bits=9, far_bits=2)[0]
+    assert 'load_p' not in info['src'] and 'cpa16(&tile' in info['src']
+    monkeypatch.delenv('DNM_JIT_TMA')
+    monkeypatch.setenv('DNM_JIT_TMA_REDUCE', '0')
+    info = check(tmp_path, 'heisenberg', 14, tile_bits=9, far_bits=2)[0]
+    assert 'load_p' in info['src'] and 'reduce_p' not in info['src']
+
+
+def test_pipelined_ring(tmp_path):
+    """Persistent CTAs: 3 CTAs walk 32 tiles, every ring slot and both barrier phases are reused."""
+    info = check(tmp_path, 'MBL', 14, tile_bits=9, far_bits=2, pipeline=1)[0]
+    assert info['pipelined'] >= 1 and 'mbar_wait(&full[b], phase)' in info['src']
+
+
+def test_parity_subspace(tmp_path):
+    check(tmp_path, 'heisenberg', 15, sub=Parity('even', L=15), tile_bits=9, far_bits=2)
+    check(tmp_path, 'MBL', 15, sub=Parity('odd', L=15), tile_bits=9, far_bits=2)
+
+
+@pytest.mark.parametrize('name,nranks', [('MBL', 2), ('long_range', 4), ('heisenberg', 4), ('XX', 2)])
+def test_folded_remote_masks_read_the_peer_shards(tmp_path, name, nranks):
+    """Sharded MatMult in fold mode: every rank's passes read the partner shards through Peers."""
+    L = 13 + nranks.bit_length() - 1
+    infos = check(tmp_path, name, L, nranks=nranks, tile_bits=9, far_bits=2)
+    for info in infos:
+        assert info['remote'] >= 1 and 'xs.p[' in info['src']
+
+
+def test_emulation_switch_does_not_leak(tmp_path):
+    """After the switch is cleared the generator emits the CUDA source again, byte for byte."""
+    a = dryrun('MBL', 24)
+    Emulated(tmp_path, 'MBL', 14, 'leak', tile_bits=9, far_bits=2)
+    b = dryrun('MBL', 24)
+    assert a['src'] == b['src'] and b['cubin'] > 0
+    assert not re.search(r'emu_|pthread', b['src'])

@@ -78,3 +78,13 @@ def test_parity_subspace_and_pipelined_variant_compile():
 def test_non_lean_operator_generates_nothing():
     r = dryrun('SYK', 12, sub=Parity('even', L=12))
     assert r['kernels'] == 0 and r['cubin'] == 0
+
+
+def test_committed_samples_are_what_the_generator_emits():
+    """csrc/generated_samples/*.cu are the sources that were measured on the B200 (profiles/r02_*): a change to
+    the generator that alters them has to be re-measured, so it must show up here first."""
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'dynamite_b200', 'csrc',
+                        'generated_samples')
+    assert dryrun('MBL', 30)['src'] == open(os.path.join(root, 'mbl_L30_default.cu')).read()
+    assert dryrun('MBL', 30, pipeline=1)['src'] == open(os.path.join(root, 'mbl_L30_pipelined_tma.cu')).read()
