@@ -532,12 +532,17 @@ extern "C" int dnm_vec_create(int64_t n, dnm_vec_t *out)
   v->global_n = n;
   v->local_n = n / G.nranks;
   v->local_start = v->local_n * G.rank;
+  // A shard that peers map through CUDA IPC gets an allocation of its own: cudaMalloc carves requests below
+  // 2 MiB out of shared blocks, and an IPC handle names the whole block (two small vectors would then
+  // share one handle and the first close would unmap the other).
+  size_t bytes = sizeof(cplx) * (size_t)v->local_n;
+  if (G.nranks > 1) bytes = std::max<size_t>(bytes, (size_t)2 << 20);
   try {
-    if (cudaMalloc(&v->d, sizeof(cplx) * v->local_n) != cudaSuccess) {
+    if (cudaMalloc(&v->d, bytes) != cudaSuccess) {
       cudaGetLastError();
       v->d = nullptr;
       if (G.nranks == 1) pool_clear();  // parked workspace may be what is in the way
-      DNM_CHECK_CUDA(cudaMalloc(&v->d, sizeof(cplx) * v->local_n));
+      DNM_CHECK_CUDA(cudaMalloc(&v->d, bytes));
     }
     DNM_CHECK_CUDA(cudaMemsetAsync(v->d, 0, sizeof(cplx) * v->local_n, G.stream));
     if (G.nranks > 1) share_with_peers(v);
