@@ -29,8 +29,11 @@ from test_jit_generator import dryrun
 
 class Emulated:
     """One rank's generated passes, compiled for the host."""
+    built = 0
 
     def __init__(self, tmp_path, name, L, tag, **kw):
+        Emulated.built += 1
+        tag = f'{tag}_{Emulated.built}'                       # dlopen caches by path: one file per build
         lib = _capi.lib()
         assert lib.dnm_jit_set_host_emulation(1) == 0
         try:
@@ -113,6 +116,18 @@ def check(tmp_path, name, L, sub=None, nranks=1, seed=0, **kw):
 def test_generated_passes_match_oracle(tmp_path, name):
     infos = check(tmp_path, name, 14, tile_bits=9, far_bits=2)
     assert infos[0]['passes'] >= 2
+
+
+@pytest.mark.parametrize('name', ['MBL', 'long_range'])
+@pytest.mark.parametrize('tune', [0, 1, 2, 3])
+def test_autotuner_shapes(tmp_path, name, tune):
+    """The plan shapes the first-use autotuner chooses from (T = 11, 12, 13: 256..1024 threads per tile)."""
+    check(tmp_path, name, 18, tune=tune)
+
+
+def test_rank_4_boxes_and_three_passes(tmp_path):
+    info = check(tmp_path, 'heisenberg', 20, tune=3)[0]
+    assert info['passes'] == 3 and 'const int c[4]' in info['src']
 
 
 def test_far_masks_and_tma_boxes(tmp_path):
