@@ -176,3 +176,13 @@ def test_emulation_switch_does_not_leak(tmp_path):
     b = dryrun('MBL', 24)
     assert a['src'] == b['src'] and b['cubin'] > 0
     assert not re.search(r'emu_|pthread', b['src'])
+
+
+@pytest.mark.parametrize('knob', ['DNM_REMOTE_STAGE=1', 'DNM_FOLD_SPLIT=1', 'DNM_JIT_FAR_FIRST=1', 'DNM_JIT_HINTS=0',
+                                  'DNM_JIT_ROWS=4'])
+def test_opt_in_variants_compute_the_same_product(tmp_path, monkeypatch, knob):
+    """The experiment knobs of INTEGRATION.md section 6 change the schedule, never the result."""
+    key, val = knob.split('=')
+    monkeypatch.setenv(key, val)
+    check(tmp_path, 'long_range', 15, nranks=4, tile_bits=9, far_bits=2)
+    check(tmp_path, 'MBL', 15, tile_bits=9, far_bits=3)
