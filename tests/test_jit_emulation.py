@@ -186,3 +186,9 @@ def test_opt_in_variants_compute_the_same_product(tmp_path, monkeypatch, knob):
     monkeypatch.setenv(key, val)
     check(tmp_path, 'long_range', 15, nranks=4, tile_bits=9, far_bits=2)
     check(tmp_path, 'MBL', 15, tile_bits=9, far_bits=3)
+
+
+def test_c5_in_miniature_long_range_on_8_ranks(tmp_path):
+    """BASELINE config C5 (long_range, 8 GPUs) scaled down to 2^13 rows per rank: 6 cross-rank masks, 7 partners."""
+    infos = check(tmp_path, 'long_range', 16, nranks=8, tile_bits=9, far_bits=2)
+    assert all(i['remote'] >= 6 for i in infos)
