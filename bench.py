@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument('-H', default='MBL', help='Hamiltonian (benchmark.py -H choices)')
     ap.add_argument('--no-precompute-diagonal', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--e2e-batch', type=int, default=8,
+                    help='products per dnm_mat_mult_host_batch call in the pipelined end-to-end measurement (N=1; 0 = skip)')
     ap.add_argument('--extras', choices=['none', 'quick', 'full'], default='quick',
                     help='also time evolve / eigsolve configs (reported under "extras")')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='target CPU time of the cpu_baseline sample')
@@ -295,6 +297,11 @@ def fill_host_x(xh, first, n):
         np.multiply(w[first // XP + b0: first // XP + b0 + step, None], base[None, :], out=blocks[b0:b0 + step])
 
 
+def parity_blocks(first_row, nloc, S):
+    """first rows of the blocks of S rows parity_check compares: the first, one past the middle, the last"""
+    return sorted({first_row, first_row + ((nloc // 2 + 12345 * 2048) & ~(S - 1)) % nloc, first_row + nloc - S})
+
+
 def parity_check(H, L, yh, first_row, n, rows=1 << 16):
     """max relative error of sampled row blocks of this rank's y = H x (host copy `yh`, rows
     [first_row, first_row + yh.size)) against the oracle's fast path on the analytic x."""
@@ -302,17 +309,39 @@ def parity_check(H, L, yh, first_row, n, rows=1 << 16):
     omsc, osub = oracle_problem(H, L)
     S = min(rows, yh.size)
     xs, ys = reserve(n, np.complex128), reserve(n, np.complex128)
-    nloc = yh.size
     worst = 0.0
-    for first in sorted({first_row, first_row + ((nloc // 2 + 12345 * 2048) & ~(S - 1)) % nloc, first_row + nloc - S}):
+    for first in parity_blocks(first_row, yh.size, S):
         for m in np.unique(omsc.masks):
             wdw = (first ^ int(m)) & ~(S - 1)
             xs[wdw:wdw + S] = host_x(wdw, S, n)
         oracle.matmult_fast_range(omsc, osub, xs, ys, first // 2048, (first + S) // 2048, nthreads=os.cpu_count() or 1)
         got = yh[first - first_row: first - first_row + S]
         want = ys[first:first + S]
-        worst = max(worst, float(np.linalg.norm(got - want) / np.linalg.norm(want)))
+        err = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+        if not np.isfinite(err):
+            return float('inf')
+        worst = max(worst, err)
     return worst
+
+
+def pipelined_e2e(mat, xh, yh, count, units, H, L, first_row, n):
+    """`count` host-buffer products through dnm_mat_mult_host_batch (one warm call of two first: it creates the
+    second pair of device buffers); the rows parity_check samples are poisoned before the timed call."""
+    from dynamite_b200 import _capi
+    try:
+        mat.mult_host_batch([xh, xh], [yh, yh])
+        S = min(1 << 16, yh.size)
+        for first in parity_blocks(first_row, yh.size, S):
+            yh[first - first_row: first - first_row + S] = np.nan
+        t0 = time.perf_counter()
+        mat.mult_host_batch([xh] * count, [yh] * count)
+        sec = time.perf_counter() - t0
+        err = parity_check(H, L, yh, first_row, n)
+        return {'value': units * count / sec, 'steps': count, 'seconds': sec, 'parity_rel_err_vs_oracle': err,
+                'api': 'dnm_mat_mult_host_batch (%d products per call; the H2D copy of product k+1 and the D2H copy '
+                       'of product k-1 overlap product k; every product copies its input and its result)' % count}
+    except (_capi.BackendError, ValueError) as exc:
+        return {'value': None, 'error': str(exc)}
 
 
 def nvlink_kib(index):
@@ -591,6 +620,16 @@ def run_ours(args, rank, world, local_rank):
                'd2h_bytes_per_step': int(n * 16), 'steps': args.e2e_steps,
                'api': 'dnm_mat_mult_host (pinned host x -> H2D -> MatMult -> D2H -> pinned host y)'
                       if world == 1 else 'dnm_vec_set_host + dnm_mat_mult + dnm_vec_get_host per rank'}
+        if world == 1 and args.e2e_batch > 1:
+            # The same products as ONE call on a stream of host buffers: the H2D copy of product k+1 and the D2H
+            # copy of product k-1 overlap product k (full-duplex PCIe).  Every product still copies its 16 B/row
+            # in and out inside the timed region.  Kept only when its result passes the same oracle check.
+            piped = pipelined_e2e(mat, xh, yh, args.e2e_batch, units, H, L, a, n)
+            e2e['pipelined'] = piped
+            if piped.get('value') and piped['parity_rel_err_vs_oracle'] < 1e-12 and piped['value'] > e2e['value']:
+                single = {k: e2e[k] for k in ('value', 'steps', 'api')}
+                e2e.update(value=piped['value'], steps=piped['steps'], api=piped['api'], single_call=single)
+                parity = max(parity, piped['parity_rel_err_vs_oracle'])
     except _capi.BackendError as exc:
         e2e = {'value': None, 'unit': UNIT, 'error': str(exc)}
 

@@ -98,6 +98,7 @@ _SIGNATURES = {
     'dnm_mat_precompute_diagonal': (C.c_int, [_mat]),
     'dnm_mat_mult': (C.c_int, [_mat, _vec, _vec]),
     'dnm_mat_mult_host': (C.c_int, [_mat, C.c_void_p, C.c_void_p]),
+    'dnm_mat_mult_host_batch': (C.c_int, [_mat, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     'dnm_mat_norm_inf': (C.c_int, [_mat, f64p]),
     'dnm_mat_size': (C.c_int, [_mat, i64p, i64p]),
     'dnm_mat_destroy': (C.c_int, [_mat]),

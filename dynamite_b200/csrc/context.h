@@ -67,6 +67,9 @@ struct Globals {
   cudaStream_t stream2 = nullptr;  // side stream: remote (NVLink) passes overlap the local ones
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // copy streams and events of dnm_mat_mult_host_batch (created on first use)
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_batch_start = nullptr, ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   double *d_scratch = nullptr;  // SCRATCH_DOUBLES
   double *h_scratch = nullptr;  // pinned, SCRATCH_DOUBLES
   double *d_partials = nullptr; // per-block partial sums
@@ -165,4 +168,5 @@ struct dnm_mat_s {
   int launches_per_mult = 0;
   int kernel_used = 0;
   dnm_vec_t work_x = nullptr, work_y = nullptr;  // device staging for dnm_mat_mult_host
+  dnm_vec_t work_x2 = nullptr, work_y2 = nullptr;  // second pair: dnm_mat_mult_host_batch double-buffers
 };

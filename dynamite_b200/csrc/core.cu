@@ -226,6 +226,17 @@ extern "C" int dnm_finalize(void)
   cudaEventDestroy(G.ev_fork);
   cudaEventDestroy(G.ev_join);
   cudaStreamDestroy(G.stream2);
+  if (G.copy_in) cudaStreamDestroy(G.copy_in);
+  if (G.copy_out) cudaStreamDestroy(G.copy_out);
+  G.copy_in = G.copy_out = nullptr;
+  if (G.ev_batch_start) cudaEventDestroy(G.ev_batch_start);
+  G.ev_batch_start = nullptr;
+  for (int b = 0; b < 2; ++b) {
+    if (G.ev_in[b]) cudaEventDestroy(G.ev_in[b]);
+    if (G.ev_cmp[b]) cudaEventDestroy(G.ev_cmp[b]);
+    if (G.ev_out[b]) cudaEventDestroy(G.ev_out[b]);
+    G.ev_in[b] = G.ev_cmp[b] = G.ev_out[b] = nullptr;
+  }
   cudaStreamDestroy(G.stream);
   G = Globals();
   DNM_API_END

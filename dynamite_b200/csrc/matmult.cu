@@ -590,6 +590,8 @@ extern "C" int dnm_mat_destroy(dnm_mat_t A)
   tiled_free(A);
   if (A->work_x) dnm_vec_destroy(A->work_x);
   if (A->work_y) dnm_vec_destroy(A->work_y);
+  if (A->work_x2) dnm_vec_destroy(A->work_x2);
+  if (A->work_y2) dnm_vec_destroy(A->work_y2);
   for (void *p : A->owned) cudaFree(p);
   if (A->d_diag) cudaFree(A->d_diag);
   A->left.release();
@@ -670,6 +672,78 @@ extern "C" int dnm_mat_mult_host(dnm_mat_t A, const double *x_host, double *y_ho
   int rc = dnm_mat_mult(A, A->work_x, A->work_y);
   if (rc) return rc;
   DNM_CHECK_CUDA(cudaMemcpyAsync(y_host, A->work_y->d, sizeof(cplx) * A->M, cudaMemcpyDeviceToHost, G.stream));
+  DNM_CHECK_CUDA(cudaStreamSynchronize(G.stream));
+  DNM_API_END
+}
+
+// A stream of products with HOST buffers, software-pipelined over the PCIe link: while product k is
+// evaluated, the input of product k+1 travels to the device on one copy stream and the result of
+// product k-1 travels back on another (the link is full duplex), two device buffers deep on either
+// side.  One product costs max(H2D, D2H) instead of H2D + MatMult + D2H.
+extern "C" int dnm_mat_mult_host_batch(dnm_mat_t A, int64_t count, const double *const *x_hosts, double *const *y_hosts)
+{
+  DNM_API_BEGIN
+  require_init();
+  DNM_REQUIRE(A && count >= 0 && (count == 0 || (x_hosts && y_hosts)), DNM_ERR_ARG, "bad arguments to dnm_mat_mult_host_batch");
+  DNM_REQUIRE(G.nranks == 1, DNM_ERR_UNSUPPORTED, "dnm_mat_mult_host_batch is single-rank");
+  for (int64_t k = 0; k < count; ++k) DNM_REQUIRE(x_hosts[k] && y_hosts[k], DNM_ERR_ARG, "null host buffer (product %lld)", (long long)k);
+  if (count == 0) return DNM_OK;
+  dnm_vec_t *xb[2] = {&A->work_x, &A->work_x2}, *yb[2] = {&A->work_y, &A->work_y2};
+  const int nb = count > 1 ? 2 : 1;
+  for (int b = 0; b < nb; ++b) {
+    if (!*xb[b]) {
+      int rc = dnm_vec_create(A->N, xb[b]);
+      if (rc) return rc;
+    }
+    if (!*yb[b]) {
+      int rc = dnm_vec_create(A->M, yb[b]);
+      if (rc) return rc;
+    }
+  }
+  if (!G.copy_in) {
+    DNM_CHECK_CUDA(cudaStreamCreateWithFlags(&G.copy_in, cudaStreamNonBlocking));
+    DNM_CHECK_CUDA(cudaStreamCreateWithFlags(&G.copy_out, cudaStreamNonBlocking));
+    DNM_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_batch_start, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) {
+      DNM_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_in[b], cudaEventDisableTiming));
+      DNM_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_cmp[b], cudaEventDisableTiming));
+      DNM_CHECK_CUDA(cudaEventCreateWithFlags(&G.ev_out[b], cudaEventDisableTiming));
+    }
+  }
+  const size_t bytes_x = sizeof(cplx) * (size_t)A->N, bytes_y = sizeof(cplx) * (size_t)A->M;
+  // whatever happens, no copy may still be in flight on the caller's buffers when this returns
+  struct Drain {
+    ~Drain()
+    {
+      cudaStreamSynchronize(G.copy_in);
+      cudaStreamSynchronize(G.stream);
+      cudaStreamSynchronize(G.copy_out);
+    }
+  } drain;
+  // earlier work on the library stream may still use the staging vectors
+  DNM_CHECK_CUDA(cudaEventRecord(G.ev_batch_start, G.stream));
+  DNM_CHECK_CUDA(cudaStreamWaitEvent(G.copy_in, G.ev_batch_start, 0));
+  DNM_CHECK_CUDA(cudaStreamWaitEvent(G.copy_out, G.ev_batch_start, 0));
+  auto send = [&](int64_t k) {
+    const int b = (int)(k & 1);
+    if (k >= 2) DNM_CHECK_CUDA(cudaStreamWaitEvent(G.copy_in, G.ev_cmp[b], 0));  // product k-2 has consumed this buffer
+    DNM_CHECK_CUDA(cudaMemcpyAsync((*xb[b])->d, x_hosts[k], bytes_x, cudaMemcpyHostToDevice, G.copy_in));
+    DNM_CHECK_CUDA(cudaEventRecord(G.ev_in[b], G.copy_in));
+  };
+  send(0);
+  for (int64_t k = 0; k < count; ++k) {
+    const int b = (int)(k & 1);
+    if (k + 1 < count) send(k + 1);
+    DNM_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_in[b], 0));
+    if (k >= 2) DNM_CHECK_CUDA(cudaStreamWaitEvent(G.stream, G.ev_out[b], 0));  // result k-2 has left this buffer
+    int rc = dnm_mat_mult(A, *xb[b], *yb[b]);
+    if (rc) return rc;
+    DNM_CHECK_CUDA(cudaEventRecord(G.ev_cmp[b], G.stream));
+    DNM_CHECK_CUDA(cudaStreamWaitEvent(G.copy_out, G.ev_cmp[b], 0));
+    DNM_CHECK_CUDA(cudaMemcpyAsync(y_hosts[k], (*yb[b])->d, bytes_y, cudaMemcpyDeviceToHost, G.copy_out));
+    DNM_CHECK_CUDA(cudaEventRecord(G.ev_out[b], G.copy_out));
+  }
+  DNM_CHECK_CUDA(cudaStreamSynchronize(G.copy_out));
   DNM_CHECK_CUDA(cudaStreamSynchronize(G.stream));
   DNM_API_END
 }

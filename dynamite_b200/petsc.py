@@ -266,6 +266,22 @@ class Mat:
             raise ValueError('host buffers must be contiguous complex128')
         check(_capi.lib().dnm_mat_mult_host(self.handle, x.ctypes.data, y.ctypes.data))
 
+    def mult_host_batch(self, xs, ys):
+        """``ys[k] = A xs[k]`` for host numpy buffers, the copies of consecutive products overlapped with
+        one another and with the multiplies (``dnm_mat_mult_host_batch``); pinned buffers for full overlap."""
+        if len(xs) != len(ys):
+            raise ValueError('as many outputs as inputs are needed')
+        for a in list(xs) + list(ys):
+            if not (a.dtype == np.complex128 and a.flags.c_contiguous):
+                raise ValueError('host buffers must be contiguous complex128')
+        for y in ys:
+            if any(np.may_share_memory(y, x) for x in xs):
+                raise ValueError('an output buffer aliases an input buffer')
+        n = len(xs)
+        xp = (C.c_void_p * max(n, 1))(*[x.ctypes.data for x in xs])
+        yp = (C.c_void_p * max(n, 1))(*[y.ctypes.data for y in ys])
+        check(_capi.lib().dnm_mat_mult_host_batch(self.handle, n, xp, yp))
+
     def norm(self, norm_type=None):
         if norm_type not in (None, NormType.INFINITY):
             raise BackendError(1, 'Only NORM_INFINITY is implemented for shell matrices.')

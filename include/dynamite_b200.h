@@ -193,6 +193,13 @@ int dnm_mat_mult(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y);
  * (what Mat.mult costs a caller whose Vec lives on the host).  The two device
  * work vectors are created on first use and kept until dnm_mat_destroy. */
 int dnm_mat_mult_host(dnm_mat_t A, const double *x_host, double *y_host);
+/* `count` products y_k = A x_k with HOST buffers, pipelined over the PCIe link: the H2D copy of x_(k+1)
+ * and the D2H copy of y_(k-1) run on their own streams while product k is evaluated (two device
+ * buffers deep per direction, kept until dnm_mat_destroy).  Pinned buffers (dnm_host_alloc) are needed
+ * for the copies to overlap; the x_k (and the y_k) may alias one another, an x_k must not alias a y_j.
+ * Synchronous: every y_k is complete on return.  Single rank. */
+int dnm_mat_mult_host_batch(dnm_mat_t A, int64_t count, const double *const *x_hosts,
+                            double *const *y_hosts);
 /* MATOP_NORM (NORM_INFINITY only)  _backend/bcuda_template_2.cu:275-403; cached. */
 int dnm_mat_norm_inf(dnm_mat_t A, double *nrm);
 int dnm_mat_size(dnm_mat_t A, int64_t *M, int64_t *N);
