@@ -72,3 +72,38 @@ def test_analytic_host_input_and_parity_check():
     assert bench.parity_check(H, L, y[n // 2:], n // 2, n, rows=1 << 12) < 1e-14
     y[n // 2 + 100] += 1e-6
     assert bench.parity_check(H, L, y[n // 2:], n // 2, n, rows=1 << 12) > 1e-9
+
+
+def test_pipelined_e2e_is_kept_only_when_it_passes_the_oracle_check():
+    """bench.pipelined_e2e poisons the rows parity_check samples before the timed batch call, so a call that
+    does not write the result cannot inherit the single call's; here the 'GPU' is the oracle."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import bench
+    import oracle
+    from dynamite_b200.hamiltonians import build_hamiltonian
+    L = 18
+    n = 1 << L
+    H = build_hamiltonian('MBL', L)
+    omsc, osub = bench.oracle_problem(H, L)
+    x = np.empty(n, dtype=np.complex128)
+    bench.fill_host_x(x, 0, n)
+    y = np.zeros(n, dtype=np.complex128)
+
+    class Good:
+        calls = []
+
+        def mult_host_batch(self, xs, ys):
+            self.calls.append(len(xs))
+            for xi, yi in zip(xs, ys):
+                yi[:] = oracle.matmult_fast(omsc, osub, xi, nthreads=4)[0]
+
+    class Lazy:
+        def mult_host_batch(self, xs, ys):
+            pass
+
+    good = bench.pipelined_e2e(Good(), x, y, 4, 1.0, H, L, 0, n)
+    assert Good.calls == [2, 4] and good['steps'] == 4 and good['value'] > 0
+    assert good['parity_rel_err_vs_oracle'] < 1e-14
+    lazy = bench.pipelined_e2e(Lazy(), x, y, 4, 1.0, H, L, 0, n)     # y still holds the right answer ... minus the poison
+    assert lazy['parity_rel_err_vs_oracle'] == float('inf')
