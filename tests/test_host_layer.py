@@ -173,3 +173,36 @@ def test_xparity_validation():
     assert np.array_equal(x.idx_to_state(np.arange(3)), np.array([0b0011, 0b0101, 0b0110]))
     with pytest.raises(ValueError):
         x.state_to_idx(0b1100)
+
+
+def test_mult_host_batch_argument_checks_and_pointer_tables(monkeypatch):
+    """Mat.mult_host_batch validates its buffers on the host and hands the C ABI two tables of pointers."""
+    from dynamite_b200 import petsc
+    seen = {}
+
+    class FakeLib:
+        @staticmethod
+        def dnm_mat_mult_host_batch(handle, n, xp, yp):
+            seen['n'] = n
+            seen['x'] = [xp[i] for i in range(n)]
+            seen['y'] = [yp[i] for i in range(n)]
+            return 0
+
+    monkeypatch.setattr(petsc._capi, 'lib', lambda: FakeLib)
+    mat = petsc.Mat(None)
+    xs = [np.zeros(8, dtype=np.complex128) for _ in range(3)]
+    ys = [np.zeros(8, dtype=np.complex128) for _ in range(3)]
+    mat.mult_host_batch(xs, ys)
+    assert seen['n'] == 3 and seen['x'] == [x.ctypes.data for x in xs] and seen['y'] == [y.ctypes.data for y in ys]
+    mat.mult_host_batch([xs[0]] * 2, [ys[0]] * 2)          # inputs may alias inputs, outputs may alias outputs
+    assert seen['x'] == [xs[0].ctypes.data] * 2
+    mat.mult_host_batch([], [])
+    assert seen['n'] == 0
+    with pytest.raises(ValueError):
+        mat.mult_host_batch(xs, ys[:2])
+    with pytest.raises(ValueError):
+        mat.mult_host_batch([xs[0]], [xs[0]])                # a product cannot be done in place
+    with pytest.raises(ValueError):
+        mat.mult_host_batch([xs[0].astype(np.complex64)], [ys[0]])
+    with pytest.raises(ValueError):
+        mat.mult_host_batch([np.zeros(16, dtype=np.complex128)[::2]], [ys[0]])
