@@ -399,6 +399,17 @@ def run_extras(level, world, lib, args, L_main):
         lib.dnm_synchronize()
         return time.perf_counter() - t0, r
 
+    def evolve_details(out, key, s, r):
+        # which algorithm ran, how many MatMults it took, what it did to the norm, and <input|result> as a
+        # fingerprint of the result that needs no third vector
+        from dynamite_b200 import computations
+        info = computations.last_evolve
+        out[key + '_algo'] = info.get('algo')
+        out[key + '_matmults'] = info.get('matmults')
+        out[key + '_norm_drift'] = abs(r.norm() / s.norm() - 1.0)
+        ov = complex(s.dot(r))
+        out[key + '_overlap_with_input'] = [ov.real, ov.imag]
+
     def random_state(L, sub):
         s = State(L=L, subspace=sub)
         s.vec.setRandom(1)
@@ -464,6 +475,19 @@ def run_extras(level, world, lib, args, L_main):
             r = State(L=30, subspace=H.subspace)
             dt, _ = timed(lambda: H.evolve(s, 50.0 / nrm, result=r), warm=False)
             out['C3_L30_MBL_evolve_t50_over_norm_s'] = dt
+            evolve_details(out, 'C3_evolve', s, r)
+            if level == 'full' or os.environ.get('DNM_BENCH_EXPOKIT', '1') != '0':
+                # the same evolution by the sub-stepped Krylov scheme the reference uses (a basis of 6-8 vectors
+                # is what fits): the two results must describe the same state
+                try:
+                    ov = out['C3_evolve_overlap_with_input']
+                    dt, _ = timed(lambda: H.evolve(s, 50.0 / nrm, result=r, algo='expokit'), warm=False)
+                    out['C3_L30_MBL_evolve_expokit_s'] = dt
+                    evolve_details(out, 'C3_evolve_expokit', s, r)
+                    ov2 = out['C3_evolve_expokit_overlap_with_input']
+                    out['C3_evolve_overlap_difference'] = abs(complex(*ov) - complex(*ov2))
+                except Exception as exc:        # (diagnostic only: never lose the result line over it)
+                    out['C3_L30_MBL_evolve_expokit_error'] = str(exc)
             H.destroy_mat()
             del s, r
         return out
@@ -477,6 +501,7 @@ def run_extras(level, world, lib, args, L_main):
     r = State(L=L_main, subspace=H.subspace)
     dt, _ = timed(lambda: H.evolve(s, 10.0 / nrm, result=r), warm=False)
     out[f'sharded_L{L_main}_{args.H}_evolve_t10_over_norm_s'] = dt
+    evolve_details(out, f'sharded_L{L_main}_evolve', s, r)
     H.destroy_mat()
     del s, r
     Le = 26 + p
@@ -499,6 +524,7 @@ def run_extras(level, world, lib, args, L_main):
         nrm = H.infinity_norm()
         dt, _ = timed(lambda: H.evolve(s, 10.0 / nrm, result=r), warm=False)
         out['C5_L33_long_range_evolve_t10_over_norm_s'] = dt
+        evolve_details(out, 'C5_evolve', s, r)
         H.destroy_mat()
     return out
 

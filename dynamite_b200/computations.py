@@ -20,6 +20,10 @@ class MaxIterationsError(ConvergenceError):
     pass
 
 
+# what the most recent evolve() did (diagnostics: bench.py reports the MatMult count next to the seconds)
+last_evolve = {}
+
+
 def evolve(H, state, t, result=None, tol=None, ncv=None, algo=None, max_its=None):
     r"""``result = exp(-i H t) state`` (reference ``computations.py:10-126``).
     Imaginary ``t`` gives imaginary-time evolution."""
@@ -43,13 +47,15 @@ def evolve(H, state, t, result=None, tol=None, ncv=None, algo=None, max_its=None
     f = mfn.getFN()
     f.setType(SLEPc.FN.Type.EXP)
     f.setScale(-1j * t)
-    mfn.setType(algo if algo is not None else 'expokit')
+    # (the reference defaults to 'expokit'; 'auto' is expokit unless its Krylov basis does not fit the GPU)
+    mfn.setType(algo if algo is not None else 'auto')
     if ncv is not None:
         mfn.setDimensions(ncv)
     mfn.setTolerances(tol=tol, max_it=max_its)
     mfn.setFromOptions()
     mfn.setOperator(H.get_mat(subspaces=(state.subspace, state.subspace)))
     mfn.solve(state.vec, result.vec)
+    last_evolve.update(algo=mfn.type, iterations=mfn.getIterationNumber(), matmults=mfn.matmults)
 
     conv = mfn.getConvergedReason()
     if conv == SLEPc.MFN.ConvergedReason.DIVERGED_ITS:

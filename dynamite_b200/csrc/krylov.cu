@@ -26,6 +26,7 @@
 #include <cstring>
 #include <memory>
 
+#include "chebyshev.h"
 #include "context.h"
 #include "dense.h"
 #include "vecops.cuh"
@@ -263,6 +264,35 @@ struct PhaseTimer {
   }
 };
 
+// csrc/chebyshev.h on device vectors: every operation is one of the library's own vector primitives
+// (the ones dnm_vec_copy / dnm_vec_scale / dnm_vec_axpby expose) or the MatMult
+struct DeviceChebOps {
+  dnm_mat_t A;
+  dnm_vec_t x, y;
+  dnm_vec_t w[3];
+  int64_t nloc;
+  void load(int dst) { vec_copy(w[dst]->d, x->d, nloc); }
+  void mult(int src, int dst)
+  {
+    const int rc = dnm_mat_mult(A, w[src], w[dst]);
+    if (rc) throw Fail{rc};
+  }
+  void scale(int dst, double r) { vec_scale(w[dst]->d, nloc, make_double2(r, 0.0)); }
+  void axpby(int dst, double a, int src, double b)
+  {
+    vec_axpby(w[dst]->d, w[src]->d, nloc, make_double2(a, 0.0), make_double2(b, 0.0));
+  }
+  void y_set(std::complex<double> c, int src)
+  {
+    vec_copy(y->d, w[src]->d, nloc);
+    vec_scale(y->d, nloc, make_double2(c.real(), c.imag()));
+  }
+  void y_add(std::complex<double> c, int src)
+  {
+    vec_axpby(y->d, w[src]->d, nloc, make_double2(c.real(), c.imag()), make_double2(1.0, 0.0));
+  }
+};
+
 double round2(double t)
 {
   // round up to two significant digits, as expokit does with its step sizes
@@ -298,6 +328,79 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
   m = (int)std::min<int64_t>(m, N);
   // basis: y doubles as v[0]; m+1 more vectors (v[1..m] and the A*v[m] probe)
   const int64_t fit = vector_budget(nloc, N);
+
+  // Chebyshev propagator (csrc/chebyshev.h) instead of expokit: on request (algo 2 / DNM_EVOLVE_CHEB=1),
+  // and by default when the Krylov basis would have to be cut down to fit device memory -- there
+  // expokit degenerates into hundreds of short sub-steps while the expansion needs three work vectors
+  // whatever its degree.  Real-time evolution only (scale purely imaginary: the propagator is unitary).
+  {
+    const bool applicable = scale_re == 0.0 && scale_im != 0.0 && fit >= 3;
+    bool use_cheb = false;
+    if (g_evolve_algo == 2) {
+      DNM_REQUIRE(scale_re == 0.0, DNM_ERR_UNSUPPORTED, "the Chebyshev propagator serves real-time evolution only");
+      DNM_REQUIRE(fit >= 3, DNM_ERR_MEM, "not enough device memory for three work vectors");
+      use_cheb = scale_im != 0.0;
+    } else if (g_evolve_algo < 0 && applicable) {
+      const char *e = getenv("DNM_EVOLVE_CHEB");
+      use_cheb = e ? atoi(e) != 0 : (m + 1 > fit);
+    }
+    if (use_cheb) {
+      double anorm = 0, sq = 0;
+      int rc = dnm_mat_norm_inf(A, &anorm);
+      if (rc) return rc;
+      vec_sqnorm_dev(x->d, nloc, G.d_scratch);
+      fetch_doubles(G.d_scratch, &sq, 1);
+      if (sq == 0.0 || anorm == 0.0) {  // zero vector stays zero; zero operator is the identity map
+        vec_copy(y->d, x->d, nloc);
+        if (reason_out) *reason_out = DNM_CONVERGED_TOL;
+        if (its_out) *its_out = 0;
+        if (matmults_out) *matmults_out = 0;
+        return DNM_OK;
+      }
+      // rho(A) <= ||A||_inf; the margin covers the rounding of the norm's own summation
+      const double a = anorm * (1.0 + 1e-9);
+      const double eps = std::min(1e-14, tol * 1e-3);
+      const cheb::Plan plan = cheb::plan(scale_im, a, eps, max_it > 0 ? (long long)max_it * (m + 1) : -1);
+      if (plan.c.empty()) {
+        if (reason_out) *reason_out = DNM_DIVERGED_ITS;
+        if (its_out) *its_out = 0;
+        if (matmults_out) *matmults_out = 0;
+        return DNM_OK;
+      }
+      if (G.rank == 0 && getenv("DNM_QUIET") == nullptr && m + 1 > fit)
+        fprintf(stderr,
+                "[dynamite_b200] evolve: a Krylov basis of %d vectors does not fit device memory (room for %lld): "
+                "Chebyshev propagator, %zu MatMults\n",
+                m + 1, (long long)fit, plan.c.size() - 1);
+      double sq_out = 0;
+      {
+        Basis W;  // three work vectors, back to the pool when the block ends
+        W.nloc = nloc;
+        for (int j = 0; j < 3; ++j) {
+          dnm_vec_t q = pool_acquire(N);
+          W.owned.push_back(q);
+        }
+        DeviceChebOps ops{A, x, y, {W.owned[0], W.owned[1], W.owned[2]}, nloc};
+        matmults = (int)cheb::apply(ops, plan, a);
+        vec_sqnorm_dev(y->d, nloc, G.d_scratch);
+        fetch_doubles(G.d_scratch, &sq_out, 1);
+      }
+      // exp(i s A) is unitary: a norm that moved means the spectrum left [-a, a] or the recurrence broke;
+      // then the sub-stepped scheme below recomputes y from x
+      const double drift = std::fabs(std::sqrt(sq_out / sq) - 1.0);
+      if (std::isfinite(drift) && drift <= 1e-9) {
+        if (reason_out) *reason_out = DNM_CONVERGED_TOL;
+        if (its_out) *its_out = 1;
+        if (matmults_out) *matmults_out = matmults;
+        return DNM_OK;
+      }
+      if (G.rank == 0)
+        fprintf(stderr, "[dynamite_b200] evolve: Chebyshev propagator changed the norm by %.3e, falling back to expokit\n", drift);
+      DNM_REQUIRE(g_evolve_algo != 2, DNM_ERR_INTERNAL, "Chebyshev propagator lost unitarity (norm drift %.3e)", drift);
+      matmults = 0;
+    }
+  }
+
   if (m + 1 > fit) {
     DNM_REQUIRE(fit >= 3, DNM_ERR_MEM, "not enough device memory for a Krylov basis (room for %lld vectors)",
                 (long long)fit);
@@ -541,8 +644,8 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
 extern "C" int dnm_evolve_algo(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re, double scale_im, double tol, int ncv,
                                int max_it, int algo, int *reason_out, int *its_out, int *matmults_out)
 {
-  if (algo != 0 && algo != 1) {
-    set_error("algo must be 0 (Lanczos recurrence) or 1 (Arnoldi with full orthogonalisation)");
+  if (algo < -1 || algo > 2) {
+    set_error("algo must be -1 (default), 0 (expokit, Lanczos recurrence), 1 (expokit, full Arnoldi) or 2 (Chebyshev)");
     return DNM_ERR_ARG;
   }
   g_evolve_algo = algo;

@@ -37,6 +37,11 @@ class MFN:
         DIVERGED_BREAKDOWN = -2
         ITERATING = 0
 
+    # 'expokit' = sub-stepped scheme with the Lanczos recurrence, 'krylov' = the same with full Arnoldi
+    # orthogonalisation, 'chebyshev' = Jacobi-Anger expansion (real time only), 'auto' = the library's
+    # choice: expokit unless its basis would not fit device memory (include/dynamite_b200.h)
+    _ALGO = {'auto': -1, 'expokit': 0, 'krylov': 1, 'chebyshev': 2}
+
     def create(self):
         self.fn = FN()
         self.type = 'expokit'
@@ -53,7 +58,7 @@ class MFN:
         return self.fn
 
     def setType(self, t):
-        if t not in ('expokit', 'krylov'):
+        if t not in self._ALGO:
             raise ValueError(f'unknown MFN type {t}')
         self.type = t
 
@@ -75,10 +80,8 @@ class MFN:
     def solve(self, b, x):
         reason, its, mm = C.c_int(), C.c_int(), C.c_int()
         a = self.fn.alpha
-        # 'expokit' = sub-stepped scheme with the Lanczos recurrence, 'krylov' = the same with full
-        # Arnoldi orthogonalisation
         check(_capi.lib().dnm_evolve_algo(self.mat.handle, b.handle, x.handle, a.real, a.imag,
-                                          self.tol, self.ncv, self.max_it, 1 if self.type == 'krylov' else 0,
+                                          self.tol, self.ncv, self.max_it, self._ALGO[self.type],
                                           C.byref(reason), C.byref(its), C.byref(mm)))
         self.reason, self.its, self.matmults = reason.value, its.value, mm.value
 

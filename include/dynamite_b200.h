@@ -260,12 +260,18 @@ enum {
  * computations.evolve gets from SLEPc.MFN type 'expokit' with FN exp scaled
  * by -i*t (computations.py:89-112).  tol<=0, ncv<=0, max_it<=0 select the
  * SLEPc defaults (1e-7, min(30,N), max(100, 2N/ncv)); ncv is additionally
- * capped by free device memory.  Outputs may be NULL. */
+ * capped by free device memory (see dnm_evolve_algo, algo -1, for what happens
+ * then).  Outputs may be NULL. */
 int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re, double scale_im,
                double tol, int ncv, int max_it, int *reason, int *its, int *matmults);
-/* The same with the MFN flavour spelled out: algo 0 = expokit sub-stepping with the Lanczos recurrence
- * (default: the operator is Hermitian), 1 = expokit sub-stepping with full Arnoldi orthogonalisation
- * (MFN type "krylov" is served by it). */
+/* The same with the algorithm spelled out: algo 0 = expokit sub-stepping with the Lanczos recurrence
+ * (the operator is Hermitian), 1 = expokit sub-stepping with full Arnoldi orthogonalisation (MFN type
+ * "krylov" is served by it), 2 = Chebyshev propagator (csrc/chebyshev.h: Jacobi-Anger expansion on
+ * [-||A||_inf, ||A||_inf], three work vectors, no inner products; real-time evolution only, i.e.
+ * scale_re == 0), -1 = what dnm_evolve does: expokit/Lanczos, unless the Krylov basis would have to be
+ * cut down to fit device memory and the evolution is in real time -- then Chebyshev
+ * (DNM_EVOLVE_CHEB=0/1 in the environment forces the choice).  A Chebyshev result whose norm moved
+ * by more than 1e-9 is discarded and recomputed by expokit (an error under algo 2). */
 int dnm_evolve_algo(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re, double scale_im,
                     double tol, int ncv, int max_it, int algo, int *reason, int *its, int *matmults);
 

@@ -124,6 +124,8 @@ def main():
             ev = H.evolve(x, t, tol=1e-12)
             ref = scipy.sparse.linalg.expm_multiply(-1j * t * A, xfull)
             check(f'evolve {name}', rel_err(ev.vec[a:b], ref[a:b]) < 1e-10, f'err={rel_err(ev.vec[a:b], ref[a:b]):.2e}')
+            ec = H.evolve(x, t, algo='chebyshev')
+            check(f'evolve chebyshev {name}', rel_err(ec.vec[a:b], ref[a:b]) < 1e-10, f'err={rel_err(ec.vec[a:b], ref[a:b]):.2e}')
             evals, evecs = H.eigsolve(nev=3, getvecs=True, tol=1e-11)
             w = scipy.sparse.linalg.eigsh(A, k=3, which='SA')[0]
             check(f'eigsolve {name}', abs(evals[0] - w.min()) < 1e-9, f'{evals[:3]} vs {np.sort(w)}')
