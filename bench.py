@@ -406,9 +406,9 @@ def run_extras(level, world, lib, args, L_main):
         info = computations.last_evolve
         out[key + '_algo'] = info.get('algo')
         out[key + '_matmults'] = info.get('matmults')
-        out[key + '_norm_drift'] = abs(r.norm() / s.norm() - 1.0)
+        out[key + '_norm_drift'] = float(abs(r.norm() / s.norm() - 1.0))
         ov = complex(s.dot(r))
-        out[key + '_overlap_with_input'] = [ov.real, ov.imag]
+        out[key + '_overlap_with_input'] = [float(ov.real), float(ov.imag)]
 
     def random_state(L, sub):
         s = State(L=L, subspace=sub)
