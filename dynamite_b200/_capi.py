@@ -110,6 +110,7 @@ _SIGNATURES = {
                              C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'dnm_evolve_algo': (C.c_int, [_mat, _vec, _vec, C.c_double, C.c_double, C.c_double, C.c_int,
                                   C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'dnm_evolve_last_algo': (C.c_int, []),
     'dnm_eigsolve': (C.c_int, [_mat, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint64,
                                C.c_int, C.POINTER(C.c_int), f64p, f64p, C.POINTER(_vec),
                                C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

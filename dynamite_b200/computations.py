@@ -55,7 +55,7 @@ def evolve(H, state, t, result=None, tol=None, ncv=None, algo=None, max_its=None
     mfn.setFromOptions()
     mfn.setOperator(H.get_mat(subspaces=(state.subspace, state.subspace)))
     mfn.solve(state.vec, result.vec)
-    last_evolve.update(algo=mfn.type, iterations=mfn.getIterationNumber(), matmults=mfn.matmults)
+    last_evolve.update(algo=mfn.used, requested=mfn.type, iterations=mfn.getIterationNumber(), matmults=mfn.matmults)
 
     conv = mfn.getConvergedReason()
     if conv == SLEPc.MFN.ConvergedReason.DIVERGED_ITS:

@@ -309,6 +309,10 @@ typedef std::complex<double> cd;
 
 // orthogonalisation requested through dnm_evolve_algo for the next dnm_evolve: -1 = default
 static int g_evolve_algo = -1;
+// what the most recent dnm_evolve ran: 0 expokit/Lanczos, 1 expokit/Arnoldi, 2 Chebyshev (-1: none yet)
+static int g_evolve_last = -1;
+
+extern "C" int dnm_evolve_last_algo(void) { return g_evolve_last; }
 
 extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re, double scale_im, double tol, int ncv,
                           int max_it, int *reason_out, int *its_out, int *matmults_out)
@@ -389,6 +393,7 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
       // then the sub-stepped scheme below recomputes y from x
       const double drift = std::fabs(std::sqrt(sq_out / sq) - 1.0);
       if (std::isfinite(drift) && drift <= 1e-9) {
+        g_evolve_last = 2;
         if (reason_out) *reason_out = DNM_CONVERGED_TOL;
         if (its_out) *its_out = 1;
         if (matmults_out) *matmults_out = matmults;
@@ -475,6 +480,7 @@ extern "C" int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re
   // classical Gram-Schmidt + DGKS refinement)
   const char *orth_env = getenv("DNM_EVOLVE_ORTH");
   const bool lanczos = g_evolve_algo >= 0 ? g_evolve_algo == 0 : !(orth_env && !strcmp(orth_env, "full"));
+  g_evolve_last = lanczos ? 0 : 1;
   // CUDA-graph capture of the basis construction: opt-in (DNM_EVOLVE_GRAPH=1).  Measured on C1 (L=20,
   // scripts/explore_c1.py): once pool_release stopped calling cudaMemGetInfo per vector the plain launch
   // sequence takes 4.7 ms per evolve, while capturing + instantiating a graph per call costs 5-70 ms.

@@ -84,6 +84,7 @@ class MFN:
                                           self.tol, self.ncv, self.max_it, self._ALGO[self.type],
                                           C.byref(reason), C.byref(its), C.byref(mm)))
         self.reason, self.its, self.matmults = reason.value, its.value, mm.value
+        self.used = {0: 'expokit', 1: 'krylov', 2: 'chebyshev'}.get(_capi.lib().dnm_evolve_last_algo(), self.type)
 
     def getConvergedReason(self):
         return self.reason

@@ -274,6 +274,8 @@ int dnm_evolve(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re, double sc
  * by more than 1e-9 is discarded and recomputed by expokit (an error under algo 2). */
 int dnm_evolve_algo(dnm_mat_t A, dnm_vec_t x, dnm_vec_t y, double scale_re, double scale_im,
                     double tol, int ncv, int max_it, int algo, int *reason, int *its, int *matmults);
+/* Which algorithm the most recent dnm_evolve / dnm_evolve_algo ran (0, 1, 2 as above; -1 before the first). */
+int dnm_evolve_last_algo(void);
 
 /* Hermitian eigensolve by thick-restart Lanczos (Krylov-Schur), i.e. what
  * computations.eigsolve gets from SLEPc.EPS HEP with the default solver

@@ -48,13 +48,20 @@ def test_chebyshev_selection_and_limits(gpu, monkeypatch):
     H = build_hamiltonian('heisenberg', L)
     x = State(L=L, state='random', seed=2)
     t = 30.0 / H.infinity_norm()
+    from dynamite_b200 import computations
     ref = H.evolve(x, t, tol=1e-13, algo='expokit').to_numpy()
+    assert computations.last_evolve['algo'] == 'expokit'
     assert rel_err(H.evolve(x, t, algo='chebyshev').to_numpy(), ref) < 1e-10
+    assert computations.last_evolve['algo'] == 'chebyshev' and computations.last_evolve['iterations'] == 1
+    z = 30.0 * (1 + 1e-9)
+    assert z < computations.last_evolve['matmults'] < z + 12 * (z + 1) ** (1 / 3) + 40
     # the default takes the expokit path while the basis fits ...
     assert rel_err(H.evolve(x, t, tol=1e-13).to_numpy(), ref) < 1e-10
+    assert computations.last_evolve['algo'] == 'expokit' and computations.last_evolve['requested'] == 'auto'
     # ... and the propagator when told to through the environment
     monkeypatch.setenv('DNM_EVOLVE_CHEB', '1')
     assert rel_err(H.evolve(x, t).to_numpy(), ref) < 1e-10
+    assert computations.last_evolve['algo'] == 'chebyshev'
     monkeypatch.delenv('DNM_EVOLVE_CHEB')
     # imaginary time is not unitary: the propagator refuses, the default still serves it
     with pytest.raises(petsc.Error):
