@@ -64,7 +64,7 @@ def _hermitian(n, seed, norm):
 
 
 @pytest.mark.parametrize('n,s,norm', [(24, -1.0, 14.0), (40, -50.0 / 7.3, 7.3), (40, 50.0 / 7.3, 7.3), (16, -0.01, 3.0),
-                                      (32, -400.0, 1.0), (8, 0.0, 2.0)])
+                                      (32, -400.0, 1.0), (8, 0.0, 2.0), (8, 5000.0, 1.0), (12, 1e-9, 3.0)])
 def test_propagator_vs_expm(cheb, n, s, norm):
     A = np.ascontiguousarray(_hermitian(n, n, norm))
     rng = np.random.default_rng(1)
