@@ -15,7 +15,8 @@ from dynamite_b200.subspaces import Full, Parity
 
 
 def dryrun(name, L, sub=None, nranks=1, rank=0, tile_bits=0, far_bits=-1, pipeline=0, tune=-1):
-    H = build_hamiltonian(name, L)
+    """`name`: a benchmark model of hamiltonians.py, or an Operator"""
+    H = build_hamiltonian(name, L) if isinstance(name, str) else name
     H.reduce_msc()
     masks, offs = msc_tools.mask_offsets(H.msc)
     masks, offs = _capi.as_i64(masks), _capi.as_i64(offs)
