@@ -433,8 +433,11 @@ void gen_classic(Out &o, const PassDesc &pd, int index)
   if (getenv("DNM_JIT_MINB")) minb = std::max(1, std::min(minb, atoi(getenv("DNM_JIT_MINB"))));
   const int nrem = pd.stage_remote ? remote_groups(pd) : 0;
   const bool tma = pd.tma_stage;
-  const bool tma_reduce = tma && pd.tma_reduce && P.accumulate == 1;
   const Box bx = tile_box(pd);
+  // (an accumulating pass whose window is the contiguous tile has no tensor box to reduce into: it keeps the
+  // read-modify-write epilogue -- found by the emulation fuzz, such a pass used to be emitted with a 0-d tensor
+  // reduce that NVRTC rejects, which cost the whole plan its generated kernels)
+  const bool tma_reduce = tma && pd.tma_reduce && P.accumulate == 1 && bx.rank > 0;
   o("// ---- pass %d (classic%s): T=%d R=%d, %d groups, %s, far_bits=%d\n", index, tma ? ", TMA staging" : "", g.T, R, P.ngroups,
     P.accumulate ? "accumulate" : "write", P.far_bits);
   if (tma) emit_tma_helpers(o, pd, index, bx, tma_reduce);
@@ -807,6 +810,7 @@ const char *PRELUDE =
 }  // namespace
 
 bool tma_eligible(const PassDesc &pd) { return tile_box(pd).rank >= 0; }
+bool tma_reducible(const PassDesc &pd) { return tile_box(pd).rank > 0; }
 
 void set_host_emulation(bool on) { g_host_emulation = on; }
 bool host_emulation() { return g_host_emulation; }

@@ -73,6 +73,8 @@ struct PassDesc {
 
 // can this window be fetched as one TMA box?
 bool tma_eligible(const PassDesc &pd);
+// ... and y can take a tensor reduce-add of the result tile (the contiguous tile has no tensor map)
+bool tma_reducible(const PassDesc &pd);
 
 // tests: emit the same kernel bodies for a C++ compiler (CUDA vocabulary emulated by the prelude)
 void set_host_emulation(bool on);

@@ -1447,7 +1447,7 @@ TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false, int tune = -1)
       // Measured on B200 (profiles/r02_experiments.md §5): with 8-16 resident warps per SM the
       // persistent kernel cannot hide the L2 latency of the FAR loads and loses to one tile per CTA
       // (4 CTAs per SM at T=11); it stays opt-in (option pipeline = 1).
-      d.pipelined = A->pipeline == 1 && jit::tma_eligible(d) &&
+      d.pipelined = A->pipeline == 1 && jit::tma_eligible(d) && (ps.p.accumulate != 1 || jit::tma_reducible(d)) &&
                     ring <= 232448 && (ps.peer_xor == 0 || best->dma);
       descs.push_back(d);
       which.push_back(k);

@@ -271,3 +271,16 @@ def test_random_two_pattern_operators(tmp_path, seed):
         check(tmp_path, random_pair_operator(L, seed), L, nranks=2, seed=seed, **kw)
     except NotGenerated:
         pytest.skip('groups collided into a mask with more than two sign patterns: a pass keeps the generic kernel')
+
+
+def test_contiguous_accumulating_pass(tmp_path):
+    """Found by fuzzing this file's checks: when the window of an ACCUMULATING pass is the contiguous tile there is
+    no tensor box for the reduce-add epilogue; the generator used to emit a 0-d tensor reduce that NVRTC rejects
+    (the plan then silently lost its generated kernels).  Such a pass keeps the read-modify-write epilogue."""
+    H = random_pauli_operator(16, 1022, nstrings=20)
+    cuda = dryrun(H, 16, tile_bits=13, far_bits=0)
+    assert cuda['cubin'] > 0 and cuda['kernels'] == cuda['passes'] == 2
+    assert 'accumulate' in cuda['src'] and 'cp.reduce.async.bulk.tensor' not in cuda['src']
+    check(tmp_path, random_pauli_operator(16, 1022, nstrings=20), 16, seed=1, tile_bits=13, far_bits=0)
+    piped = dryrun(random_pauli_operator(16, 1022, nstrings=20), 16, tile_bits=13, far_bits=0, pipeline=1)
+    assert piped['cubin'] > 0           # (the persistent variant leaves that pass to the classic kernel)
