@@ -1491,8 +1491,13 @@ TiledPlan *build_plan(dnm_mat_s *A, bool no_fold = false, int tune = -1)
           return build_plan(A, true, tune);
         }
         if (A->verbose) fprintf(stderr, "[dnm] %zu generated kernels (%zu bytes of source)\n", which.size(), src.size());
-      } else if (A->verbose || A->jit == 1) {
-        fprintf(stderr, "[dnm] generated kernels unavailable, using the generic tiled kernel: %s\n", log.c_str());
+      } else {
+        // NVRTC or the driver entry points missing is an environment matter (quiet unless asked); a source that
+        // NVRTC REJECTS is a generator defect that costs the plan its fast kernels: never silent
+        const bool env = log.find("could not be loaded") != std::string::npos || log.find("unavailable") != std::string::npos;
+        if (A->verbose || A->jit == 1 || (!env && G.rank == 0 && getenv("DNM_QUIET") == nullptr))
+          fprintf(stderr, "[dynamite_b200] generated kernels %s, using the generic tiled kernel: %.600s\n",
+                  env ? "unavailable" : "REJECTED by the compiler (generator defect)", log.c_str());
       }
     }
   }
