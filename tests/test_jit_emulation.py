@@ -284,3 +284,10 @@ def test_contiguous_accumulating_pass(tmp_path):
     check(tmp_path, random_pauli_operator(16, 1022, nstrings=20), 16, seed=1, tile_bits=13, far_bits=0)
     piped = dryrun(random_pauli_operator(16, 1022, nstrings=20), 16, tile_bits=13, far_bits=0, pipeline=1)
     assert piped['cubin'] > 0           # (the persistent variant leaves that pass to the classic kernel)
+
+
+def test_the_default_L30_shape_with_its_full_L2_window(tmp_path):
+    """(T, run bits, far) = (11, 4, 10), the shape the autotuner keeps for the L=30 MBL benchmark: at L=22 the
+    writing pass has the same 20 groups, half of them FAR loads over ten index positions."""
+    info = check(tmp_path, 'MBL', 22, tune=0)[0]
+    assert 'far_bits=10' in info['src'] and info['src'].count(' FAR') >= 10
