@@ -206,3 +206,37 @@ def test_mult_host_batch_argument_checks_and_pointer_tables(monkeypatch):
         mat.mult_host_batch([xs[0].astype(np.complex64)], [ys[0]])
     with pytest.raises(ValueError):
         mat.mult_host_batch([np.zeros(16, dtype=np.complex128)[::2]], [ys[0]])
+
+
+def test_mfn_type_reaches_the_c_abi(monkeypatch):
+    """The MFN shim passes the algorithm the caller named (-1 = the library's choice) and reports the one that ran."""
+    from dynamite_b200 import slepc
+    calls = []
+
+    class FakeLib:
+        @staticmethod
+        def dnm_evolve_algo(mat, b, x, are, aim, tol, ncv, max_it, algo, reason, its, mm):
+            calls.append((are, aim, tol, ncv, max_it, algo))
+            reason._obj.value, its._obj.value, mm._obj.value = 1, 1, 87
+            return 0
+
+        @staticmethod
+        def dnm_evolve_last_algo():
+            return 2
+
+    class Handle:
+        handle = None
+
+    monkeypatch.setattr(slepc._capi, 'lib', lambda: FakeLib)
+    for name, code in (('auto', -1), ('expokit', 0), ('krylov', 1), ('chebyshev', 2)):
+        mfn = slepc.MFN().create()
+        mfn.getFN().setScale(-1j * 0.5)
+        mfn.setType(name)
+        mfn.setTolerances(tol=1e-9, max_it=7)
+        mfn.setDimensions(12)
+        mfn.setOperator(Handle())
+        mfn.solve(Handle(), Handle())
+        assert calls[-1] == (0.0, -0.5, 1e-9, 12, 7, code)
+        assert mfn.used == 'chebyshev' and mfn.matmults == 87 and mfn.getConvergedReason() == 1
+    with pytest.raises(ValueError):
+        slepc.MFN().create().setType('pade')
